@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""bench.py -- point-pair distance evals/sec (fwd+bwd) of the HiT-ADV geometry hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl hitgeom|reference] [--workload c5shard|c1]
+    torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+A "step" is one forward+backward of the CW-kNN distance term (`ChamferkNNDist`, CW/kNN.py:104-108) over one
+batch of synthetic clouds.  Default workload = BASELINE.json config 5's per-GPU shard: 1024 clouds x 16384
+points per GPU (8192 clouds over 8 GPUs), Chamfer (both directions) + kNN-outlier -> 2*B*N^2 algorithmic
+pair-evals per step; the backward reuses saved indices and adds none.  Weak scaling:
+per-GPU work is fixed, instances are sharded, no collective on the data path.
+
+Timing: CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks.  Inputs
+(402 MB per rank) exceed the 126 MB L2, so no flush is needed for c5shard; the small c1 workload flushes L2
+between timed iterations.  One JSON line is printed by rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "hit-adv_b200"), os.path.join(ROOT, "tests")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "point-pair distance evals/sec (fwd+bwd)"
+UNIT = "pair-evals/s"
+FLOP_PER_PAIR = 8.0  # 4 FFMA-equivalents per pair-eval (SURVEY.md section 8d / BASELINE.md section 3)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="hitgeom", choices=["hitgeom", "reference"])
+    ap.add_argument("--workload", default="c5shard", choices=["c5shard", "c1"])
+    ap.add_argument("--clouds", type=int, default=0, help="clouds per GPU (default: workload's)")
+    ap.add_argument("--points", type=int, default=0, help="points per cloud (default: workload's)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=20.0, help="CPU-baseline budget")
+    return ap.parse_args()
+
+
+def workload_shape(args):
+    if args.workload == "c1":
+        B, N = 388, 1024
+        name = "C1: ChamferDist+HausdorffDist+KNNDist(k=5) fwd+bwd, 388x1024 clouds vs jittered copies"
+    else:
+        B, N = 1024, 16384
+        name = ("C5 shard: ChamferkNNDist (Chamfer both directions + kNN-outlier k=5) fwd+bwd, "
+                "1024 clouds x 16384 points per GPU (8192 clouds over 8 GPUs)")
+    return (args.clouds or B), (args.points or N), name
+
+
+def make_clouds(B, N, seed):
+    """N(0,I) clouds, centred, max-norm 1; adv = ori + clamp(0.01 randn, +-0.05)."""
+    rng = np.random.default_rng(seed)
+    ori = rng.standard_normal((B, N, 3), dtype=np.float32)
+    ori -= ori.mean(axis=1, keepdims=True)
+    ori /= np.sqrt((ori * ori).sum(-1)).max(axis=1)[:, None, None]
+    adv = ori + np.clip(0.01 * rng.standard_normal((B, N, 3), dtype=np.float32), -0.05, 0.05)
+    return np.ascontiguousarray(ori, dtype=np.float32), np.ascontiguousarray(adv, dtype=np.float32)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md's clocks line)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        self.mark0 = self.mark1 = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def begin(self):
+        self.mark0 = time.time()
+
+    def end(self):
+        self.mark1 = time.time()
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if self.mark0 is not None and self.mark0 <= t <= (self.mark1 or t) + 0.1]
+        if not rows:
+            rows = [r for _, r in self.rows[-3:]]
+        sm, reasons, mx = [], set(), None
+        for r in rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return json.load(open(path)), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------------------
+# CPU reference arm / baseline: the reference's torch program (oracle/torch_port.py) on the host cores
+# ------------------------------------------------------------------------------------------------------------
+def cpu_step_fn(workload):
+    from oracle import torch_port as tp
+
+    return tp.step_cd_hd_knn if workload == "c1" else tp.step_chamfer_knn
+
+
+def pairs_per_cloud(N):
+    return 2.0 * N * N
+
+
+def cpu_sample_plan(N, budget_s, workload):
+    """How many clouds of how many points one CPU sample holds: the real N if the [N,N] FP32 matrices of the
+    reference path (about a dozen live copies incl. autograd) fit in host RAM, else the largest power of two."""
+    try:
+        import psutil
+
+        free = psutil.virtual_memory().available
+    except Exception:
+        free = 32 << 30
+    n = N
+    while n > 1024 and 14 * 4 * n * n > 0.5 * free:
+        n //= 2
+    return n
+
+
+def run_cpu(workload, N, budget_s, steps=None, warmup=0):
+    """Times the reference's CPU torch path on a bounded sample; returns dict(value, cores, sample, ms_per_step)."""
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    step = cpu_step_fn(workload)
+    n = cpu_sample_plan(N, budget_s, workload)
+    # calibrate on one small cloud to choose the clouds-per-sample
+    ori, adv = make_clouds(1, min(n, 2048), 4321)
+    t0 = time.time()
+    step(torch.from_numpy(adv), torch.from_numpy(ori))
+    rate = pairs_per_cloud(min(n, 2048)) / max(time.time() - t0, 1e-4)
+    per_cloud_s = pairs_per_cloud(n) / rate
+    if steps is None:
+        clouds = int(max(1, min(64, budget_s / max(per_cloud_s, 1e-3))))
+        steps, warmup = 1, 0
+    else:
+        clouds = int(max(1, min(16, (budget_s / max(steps + warmup, 1)) / max(per_cloud_s, 1e-3))))
+    ori, adv = make_clouds(clouds, n, 1234)
+    ori_t, adv_t = torch.from_numpy(ori), torch.from_numpy(adv)
+
+    def one():
+        if n >= 8192:  # one cloud at a time: the reference path needs ~1 GiB per [N,N] matrix at N=16384
+            for c in range(clouds):
+                step(adv_t[c : c + 1], ori_t[c : c + 1])
+        else:
+            step(adv_t, ori_t)
+
+    for _ in range(warmup):
+        one()
+    t0 = time.time()
+    for _ in range(steps):
+        one()
+    dt = (time.time() - t0) / steps
+    sample = f"{clouds} cloud(s) x {n} points per step, {steps} step(s)" + ("" if n == N else f" (N reduced from {N}: host RAM)")
+    return {"value": clouds * pairs_per_cloud(n) / dt, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+            "ms_per_step": dt * 1e3}
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    B, N, name = workload_shape(args)
+    r = run_cpu(args.workload, N, budget_s=max(30.0, 12.0 * (args.steps + args.warmup)), steps=args.steps,
+                warmup=args.warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": name, "clouds_per_gpu": B, "points": N,
+                       "note": "reference CPU torch path (oracle/torch_port.py restatement) on the host cores"},
+            "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# hitgeom arm
+# ------------------------------------------------------------------------------------------------------------
+def main_hitgeom(args):
+    from hitgeom import _lib, sharding
+    from hitgeom.dist_utils import ChamferDist, ChamferkNNDist, HausdorffDist, KNNDist
+
+    rank, world, local = sharding.init()
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    _lib.lib()  # fail loudly if the CUDA extension is missing
+    B, N, name = workload_shape(args)
+    ori_np, adv_np = make_clouds(B, N, 1234 + rank)
+    ori_h = torch.from_numpy(ori_np).pin_memory()
+    adv_h = torch.from_numpy(adv_np).pin_memory()
+    grad_h = torch.empty_like(adv_h).pin_memory()
+    ori_d = ori_h.to(dev, non_blocking=True)
+    adv_d = adv_h.to(dev, non_blocking=True).requires_grad_()
+
+    if args.workload == "c1":
+        cd, hd, kd = ChamferDist(), HausdorffDist(), KNNDist(k=5)
+
+        def fwd_bwd():
+            adv_d.grad = None
+            loss = cd(adv_d, ori_d) + hd(adv_d, ori_d) + kd(adv_d)
+            loss.backward()
+            return loss
+    else:
+        dist_func = ChamferkNNDist()
+
+        def fwd_bwd():
+            adv_d.grad = None
+            loss = dist_func(adv_d, ori_d)
+            loss.backward()
+            return loss
+
+    pairs_step = B * pairs_per_cloud(N)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if args.workload == "c1" else None
+
+    def l2_flush():
+        if flush is not None:
+            flush.zero_()
+
+    for _ in range(max(args.warmup, 3)):
+        fwd_bwd()
+    torch.cuda.synchronize()
+
+    # ---- device-resident timing ---------------------------------------------------------------------------
+    sampler = ClockSampler(local) if rank == 0 else None
+    sharding.barrier()
+    torch.cuda.synchronize()
+    _lib.prof_enable(True)
+    launches0 = _lib.launch_count()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    if sampler:
+        sampler.begin()
+    for s, e in evs:
+        l2_flush()
+        s.record()
+        fwd_bwd()
+        e.record()
+    torch.cuda.synchronize()
+    if sampler:
+        sampler.end()
+    sharding.barrier()
+    launches = (_lib.launch_count() - launches0) // args.steps
+    ms_local = sum(s.elapsed_time(e) for s, e in evs) / args.steps
+    ms = sharding.max_over_ranks(ms_local)
+    nn_ms, nn_n = _lib.prof_read("nn_bidir")
+    knn_ms, knn_n = _lib.prof_read("knn")
+    _lib.prof_enable(False)
+    clocks = sampler.stop() if sampler else {}
+
+    # ---- end-to-end: host buffers in, gradient + loss back to the host, every step ---------------------------
+    def e2e_step():
+        with torch.no_grad():
+            adv_d.copy_(adv_h, non_blocking=True)
+            ori_d.copy_(ori_h, non_blocking=True)
+        loss = fwd_bwd()
+        grad_h.copy_(adv_d.grad, non_blocking=True)
+        return float(loss.item())
+
+    e2e_step()
+    sharding.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        l2_flush()
+        e2e_step()
+    e1.record()
+    torch.cuda.synchronize()
+    sharding.barrier()
+    e2e_ms = sharding.max_over_ranks(e0.elapsed_time(e1) / args.steps)
+
+    if rank != 0:
+        return
+    pk, pk_src = peaks()
+    info = _lib.device_info()
+    sm_max_mhz = float(clocks.get("sm_max_mhz") or pk.get("sm_max_mhz") or info["clock_khz"] / 1e3)
+    fp32_peak_tflops = info["sm_count"] * 128 * 2 * sm_max_mhz * 1e6 / 1e12
+    # dominant kernel = the tagged hot kernel with the larger share of the step
+    tagged = {"nn_bidir_d3_kernel": (nn_ms, nn_n, B * float(N) * N), "knn3_kernel": (knn_ms, knn_n, B * float(N) * N)}
+    kname = max(tagged, key=lambda k: tagged[k][0])
+    k_ms, k_n, k_pairs = tagged[kname]
+    k_avg_ms = k_ms / max(k_n, 1)
+    achieved = k_pairs * FLOP_PER_PAIR / (k_avg_ms * 1e-3) / 1e12 if k_avg_ms > 0 else 0.0
+    alg_bytes = B * (2 * N) * 12 + B * (2 * N) * 8
+    roofline = {
+        "bound": "fp32", "kernel": kname, "achieved": achieved, "peak": fp32_peak_tflops, "unit": "TFLOP/s",
+        "frac": achieved / fp32_peak_tflops if fp32_peak_tflops else None, "traffic": None,
+        "peak_source": f"computed {info['sm_count']} SMs x 128 FP32 lanes x 2 x {sm_max_mhz:.0f} MHz (no FP32 figure in MEASURED_PEAKS.json)",
+        "avg_launch_ms": k_avg_ms, "launches_timed": k_n, "algorithmic_pair_evals_per_launch": k_pairs,
+        "flop_per_pair_eval": FLOP_PER_PAIR,
+        "shares_of_step": {k: (v[0] / max(v[1], 1)) * (v[1] / args.steps) / ms_local for k, v in tagged.items()},
+        "hbm": {"algorithmic_bytes_per_launch": alg_bytes, "achieved_gbs": alg_bytes / (k_avg_ms * 1e-3) / 1e9 if k_avg_ms > 0 else 0.0,
+                "peak_gbs": pk.get("hbm_gbs"), "peak_source": pk_src},
+    }
+    line = {
+        "metric": METRIC, "value": world * pairs_step / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": name, "clouds_per_gpu": B, "points": N, "k": 5,
+                   "l2": "inputs (402 MB/rank) exceed the 126 MB L2" if flush is None else "L2 flushed (256 MiB write) between timed iterations",
+                   "pair_evals_per_step_per_gpu": pairs_step},
+        "clocks": clocks, "roofline": roofline,
+        "e2e": {"value": world * pairs_step / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": int(adv_h.numel() * 4 + ori_h.numel() * 4),
+                "d2h_bytes_per_step": int(grad_h.numel() * 4 + 4)},
+        "gpu_launches": int(launches),
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            r = run_cpu(args.workload, N, args.cpu_seconds)
+            line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        except Exception as e:  # the baseline must never take the GPU number down with it
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        main_reference(a)
+    else:
+        main_hitgeom(a)

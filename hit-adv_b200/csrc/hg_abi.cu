@@ -1,0 +1,113 @@
+// hg_abi.cu -- version, error reporting and device queries of the C ABI (include/hitgeom.h).
+#include <stdarg.h>
+
+#include "hg_common.cuh"
+
+static thread_local char g_err[512] = "";
+
+void hg_set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+unsigned long long g_hg_launches = 0;
+
+HG_API int hg_version(void) { return 100; }
+
+HG_API unsigned long long hg_launch_count(void) { return g_hg_launches; }
+
+HG_API const char *hg_last_error(void) { return g_err; }
+
+int hg_sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (!cached[dev]) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+HG_API int hg_device_info(int *sm_count, int *clock_khz, long long *l2_bytes, long long *mem_bytes) {
+  int dev = 0;
+  HG_CUDA(cudaGetDevice(&dev));
+  int v = 0;
+  if (sm_count) {
+    HG_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev));
+    *sm_count = v;
+  }
+  if (clock_khz) {
+    HG_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrClockRate, dev));
+    *clock_khz = v;
+  }
+  if (l2_bytes) {
+    HG_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrL2CacheSize, dev));
+    *l2_bytes = v;
+  }
+  if (mem_bytes) {
+    size_t free_b = 0, total_b = 0;
+    HG_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    *mem_bytes = (long long)total_b;
+  }
+  return HG_OK;
+}
+
+// ---- optional per-kernel device timing (bench.py's roofline object) ---------------------------------------
+// When enabled, the launch of each tagged hot kernel is bracketed by CUDA events recorded on the launching
+// stream; hg_prof_read() returns the summed device time and the launch count.  Off by default (no events).
+#include <vector>
+
+namespace {
+struct ProfTag {
+  std::vector<cudaEvent_t> start, stop;
+  int used = 0;
+};
+ProfTag g_prof[HG_PROF_NTAGS];
+bool g_prof_on = false;
+constexpr int kProfMaxPairs = 4096;
+}  // namespace
+
+bool hg_prof_begin(int tag, cudaStream_t s) {
+  if (!g_prof_on || tag < 0 || tag >= HG_PROF_NTAGS) return false;
+  ProfTag &t = g_prof[tag];
+  if (t.used >= kProfMaxPairs) return false;
+  if (t.used >= (int)t.start.size()) {
+    cudaEvent_t a, b;
+    if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return false;
+    t.start.push_back(a);
+    t.stop.push_back(b);
+  }
+  cudaEventRecord(t.start[t.used], s);
+  return true;
+}
+
+void hg_prof_end(int tag, cudaStream_t s, bool began) {
+  if (!began) return;
+  ProfTag &t = g_prof[tag];
+  cudaEventRecord(t.stop[t.used], s);
+  t.used++;
+}
+
+HG_API void hg_prof_enable(int on) {
+  g_prof_on = on != 0;
+  for (int i = 0; i < HG_PROF_NTAGS; ++i) g_prof[i].used = 0;
+}
+
+HG_API int hg_prof_read(int tag, float *total_ms, int *launches) {
+  HG_REQUIRE(tag >= 0 && tag < HG_PROF_NTAGS && total_ms && launches, HG_E_BADARG, "prof_read: bad tag");
+  ProfTag &t = g_prof[tag];
+  float sum = 0.f;
+  for (int i = 0; i < t.used; ++i) {
+    HG_CUDA(cudaEventSynchronize(t.stop[i]));
+    float ms = 0.f;
+    HG_CUDA(cudaEventElapsedTime(&ms, t.start[i], t.stop[i]));
+    sum += ms;
+  }
+  *total_ms = sum;
+  *launches = t.used;
+  return HG_OK;
+}

@@ -1,0 +1,104 @@
+// hg_common.cuh -- shared helpers of libhitgeom (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/hitgeom.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libhitgeom is written for sm_100a (B200) only"
+#endif
+
+#define HG_API extern "C" __attribute__((visibility("default")))
+
+// ---- error reporting (thread-local message, never exit()) -------------------------------------------------
+void hg_set_error(const char *fmt, ...);
+
+#define HG_REQUIRE(cond, code, ...)   \
+  do {                                \
+    if (!(cond)) {                    \
+      hg_set_error(__VA_ARGS__);      \
+      return (code);                  \
+    }                                 \
+  } while (0)
+
+extern unsigned long long g_hg_launches;  // kernels launched by this library (bench.py's gpu_launches)
+
+#define HG_CHECK_LAUNCH(name)                                            \
+  do {                                                                   \
+    ++g_hg_launches;                                                     \
+    cudaError_t e__ = cudaGetLastError();                                \
+    if (e__ != cudaSuccess) {                                            \
+      hg_set_error("%s: %s", (name), cudaGetErrorString(e__));           \
+      return (int)e__;                                                   \
+    }                                                                    \
+  } while (0)
+
+#define HG_CUDA(call)                                                    \
+  do {                                                                   \
+    cudaError_t e__ = (call);                                            \
+    if (e__ != cudaSuccess) {                                            \
+      hg_set_error("%s: %s", #call, cudaGetErrorString(e__));            \
+      return (int)e__;                                                   \
+    }                                                                    \
+  } while (0)
+
+static inline cudaStream_t hg_stream(hgStream s) { return reinterpret_cast<cudaStream_t>(s); }
+
+static inline size_t hg_align(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+int hg_sm_count();
+
+// per-kernel device timing hooks (hg_abi.cu); tags are part of the ABI (include/hitgeom.h HG_PROF_*)
+bool hg_prof_begin(int tag, cudaStream_t s);
+void hg_prof_end(int tag, cudaStream_t s, bool began);
+
+// ---- exact FP32 building blocks (SURVEY.md section 8 a-bis) ------------------------------------------------
+// Everything that decides an index goes through these intrinsics, which nvcc never contracts or reorders.
+
+// torch.bmm with inner dim 3: fma(a2,b2, fma(a1,b1, a0*b0))
+__device__ __forceinline__ float hg_dot3_fma(float a0, float a1, float a2, float b0, float b1, float b2) {
+  return __fmaf_rn(a2, b2, __fmaf_rn(a1, b1, __fmul_rn(a0, b0)));
+}
+// torch.sum(x**2, dim) for three channels: (a0*a0 + a1*a1) + a2*a2, no FMA
+__device__ __forceinline__ float hg_sumsq3_seq(float a0, float a1, float a2) {
+  return __fadd_rn(__fadd_rn(__fmul_rn(a0, a0), __fmul_rn(a1, a1)), __fmul_rn(a2, a2));
+}
+// nvcc -O3 contraction of (ax-bx)*(ax-bx) + (ay-by)*(ay-by) + (az-bz)*(az-bz) in the pointnet2_ops kernels
+__device__ __forceinline__ float hg_dist3_fma(float ax, float ay, float az, float bx, float by, float bz) {
+  const float dx = __fsub_rn(ax, bx), dy = __fsub_rn(ay, by), dz = __fsub_rn(az, bz);
+  return __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+}
+
+// order-preserving float <-> uint32 (so that integer min/max atomics select the float min/max exactly)
+__device__ __forceinline__ unsigned hg_ord(float f) {
+  const unsigned u = __float_as_uint(f);
+  return u ^ (((unsigned)((int)u >> 31)) | 0x80000000u);
+}
+__device__ __forceinline__ float hg_unord(unsigned u) {
+  return __uint_as_float((u & 0x80000000u) ? (u ^ 0x80000000u) : ~u);
+}
+
+__device__ __forceinline__ float hg_warp_min_f32(float v) {
+  float m;
+  asm("redux.sync.min.f32 %0, %1, 0xffffffff;" : "=f"(m) : "f"(v));  // CREDUX.MIN.F32 (sm_100a)
+  return m;
+}
+__device__ __forceinline__ float hg_warp_max_f32(float v) {
+  float m;
+  asm("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(m) : "f"(v));
+  return m;
+}
+
+// ---- deterministic reverse map (CSR) used by every scatter-style backward ----------------------------------
+// keys [B,E] (destination of edge e, or <0 to skip) -> off [B,N+1], list [B,E] with, for each destination,
+// its edges in ascending e.  Summing in list order is what replaces the reference's float atomicAdd.
+size_t hg_csr_workspace_bytes(int B, int N, int E);
+struct HgCsr {
+  int *off;   // [B, N+1]
+  int *list;  // [B, E]
+};
+int hg_csr_build(const int *keys, int B, int E, int N, void *workspace, size_t workspace_bytes, HgCsr *out,
+                 cudaStream_t stream);

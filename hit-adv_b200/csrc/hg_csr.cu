@@ -1,0 +1,96 @@
+// hg_csr.cu -- deterministic reverse map for scatter-style backward passes.
+//
+// The reference accumulates every scatter gradient with float atomicAdd (sampling_gpu.cu:43,
+// group_points_gpu.cu:60, interpolate_gpu.cu:139-141) or with ATen index_put(accumulate=True); the sum
+// order, and therefore the low bits of the result, change from run to run.  Here each destination gets the
+// list of its source edges in ascending edge order (a stable counting sort per cloud); consumers add in
+// list order, so results are bit-reproducible.  Integer atomics (counts) are order-independent.
+#include "hg_common.cuh"
+
+namespace {
+
+constexpr int kCsrThreads = 128;
+
+__global__ void __launch_bounds__(kCsrThreads) csr_build_kernel(const int *__restrict__ keys, int E, int N,
+                                                                int *__restrict__ off_all,
+                                                                int *__restrict__ cursor_all,
+                                                                int *__restrict__ list_all) {
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int *k = keys + (size_t)b * E;
+  int *off = off_all + (size_t)b * (N + 1);
+  int *cursor = cursor_all + (size_t)b * N;
+  int *list = list_all + (size_t)b * E;
+  __shared__ int warp_tot[kCsrThreads / 32];
+  __shared__ int carry_s;
+
+  for (int i = tid; i <= N; i += kCsrThreads) off[i] = 0;
+  __syncthreads();
+  for (int e = tid; e < E; e += kCsrThreads) {
+    const int key = k[e];
+    if (key >= 0 && key < N) atomicAdd(&off[key + 1], 1);
+  }
+  if (tid == 0) carry_s = 0;
+  __syncthreads();
+  // inclusive scan of off[1..N] (off[0] stays 0) -> off[i] = #edges with key < i
+  for (int base = 1; base <= N; base += kCsrThreads) {
+    const int i = base + tid;
+    int v = (i <= N) ? off[i] : 0;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, v, d);
+      if (lane >= d) v += t;
+    }
+    if (lane == 31) warp_tot[warp] = v;
+    __syncthreads();
+    int add = carry_s;
+    for (int w = 0; w < warp; ++w) add += warp_tot[w];
+    if (i <= N) off[i] = v + add;
+    __syncthreads();
+    if (tid == kCsrThreads - 1) carry_s = v + add;
+    __syncthreads();
+  }
+  for (int i = tid; i < N; i += kCsrThreads) cursor[i] = off[i];
+  __syncthreads();
+  // stable placement by one warp: chunks of 32 edges in ascending order, rank inside the chunk by lane
+  if (warp == 0) {
+    for (int base = 0; base < E; base += 32) {
+      const int e = base + lane;
+      int key = (e < E) ? k[e] : -1;
+      if (key >= N) key = -1;
+      const unsigned same = __match_any_sync(0xffffffffu, key);
+      const int rank = __popc(same & ((1u << lane) - 1u));
+      int pos = 0;
+      if (key >= 0) pos = cursor[key] + rank;
+      __syncwarp();
+      if (key >= 0) {
+        list[pos] = e;
+        if (rank == 0) cursor[key] = pos + __popc(same);
+      }
+      __syncwarp();
+    }
+  }
+}
+
+}  // namespace
+
+size_t hg_csr_workspace_bytes(int B, int N, int E) {
+  return hg_align((size_t)B * (N + 1) * sizeof(int)) + hg_align((size_t)B * N * sizeof(int)) +
+         hg_align((size_t)B * E * sizeof(int));
+}
+
+int hg_csr_build(const int *keys, int B, int E, int N, void *workspace, size_t workspace_bytes, HgCsr *out,
+                 cudaStream_t stream) {
+  HG_REQUIRE(workspace && workspace_bytes >= hg_csr_workspace_bytes(B, N, E), HG_E_WORKSPACE,
+             "csr: workspace too small (%zu < %zu)", workspace_bytes, hg_csr_workspace_bytes(B, N, E));
+  char *p = (char *)workspace;
+  int *off = (int *)p;
+  p += hg_align((size_t)B * (N + 1) * sizeof(int));
+  int *cursor = (int *)p;
+  p += hg_align((size_t)B * N * sizeof(int));
+  int *list = (int *)p;
+  csr_build_kernel<<<B, kCsrThreads, 0, stream>>>(keys, E, N, off, cursor, list);
+  HG_CHECK_LAUNCH("csr_build_kernel");
+  out->off = off;
+  out->list = list;
+  return HG_OK;
+}

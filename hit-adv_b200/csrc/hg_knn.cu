@@ -1,0 +1,453 @@
+// hg_knn.cu -- k-nearest-neighbour selection and the kNN-outlier loss.
+//
+//   hg_knn_self_f32         util/dist_utils.py:148-156 (KNNDist) and model/dgcnn_cls.py:8-12 (DGCNN knn)
+//   hg_knn_outlier_fwd/bwd  util/dist_utils.py:157-172 and its autograd backward
+//   hg_knn_points_f32       pytorch3d.ops.knn_points (third party; semantics restated)
+//
+// Reference arithmetic (bit-exact restatement, SURVEY.md section 8 a-bis):
+//   xx_i = (p0*p0 + p1*p1) + p2*p2           torch.sum(pc**2, dim)   [ATen cascade of 16s for C >= 16]
+//   zz   = fma(p_i[C-1],p_j[C-1], ... p_i[0]*p_j[0])                 torch.matmul, sequential FMA chain
+//   dist[i,j] = (xx_j + (-2*zz)) + xx_i      (DGCNN's pairwise_distance is exactly -dist)
+// Selection: the k1 smallest per row, ascending, lowest index first among equal values (canonical order;
+// torch.topk leaves tie order unspecified).  The matrix [B,K,K] is never stored for C == 3.
+#include "hg_common.cuh"
+
+namespace {
+
+// ---- register-resident sorted list ---------------------------------------------------------------------------
+// Candidates arrive in ascending index order; a candidate enters only if strictly smaller than the current
+// last element and bubbles up while strictly smaller than its predecessor => lowest index first on ties.
+template <int KM>
+struct TopK {
+  float v[KM];
+  int id[KM];
+  __device__ __forceinline__ void init() {
+#pragma unroll
+    for (int t = 0; t < KM; ++t) {
+      v[t] = CUDART_INF_F;
+      id[t] = 0;
+    }
+  }
+  __device__ __forceinline__ void push(float d, int j) {
+    if (d < v[KM - 1]) {
+      v[KM - 1] = d;
+      id[KM - 1] = j;
+#pragma unroll
+      for (int t = KM - 1; t > 0; --t) {
+        if (v[t] < v[t - 1]) {
+          const float tv = v[t];
+          v[t] = v[t - 1];
+          v[t - 1] = tv;
+          const int ti = id[t];
+          id[t] = id[t - 1];
+          id[t - 1] = ti;
+        }
+      }
+    }
+  }
+};
+
+constexpr int kKnnThreads = 128;
+constexpr int kKnnTile = 512;
+
+enum { FORM_EXPANDED = 0, FORM_DIRECT = 1 };
+
+// One thread per query, reference points streamed through shared memory (broadcast LDS.128).
+// FORM_EXPANDED: q = refs = pc (self kNN), dist as above.  FORM_DIRECT: squared L2 of differences.
+template <int KM, int FORM, typename IdxT>
+__global__ void __launch_bounds__(kKnnThreads) knn3_kernel(const float *__restrict__ queries,
+                                                           const float *__restrict__ refs, int Nq, int Nr, int k1,
+                                                           float *__restrict__ vals, IdxT *__restrict__ idx) {
+  __shared__ float4 tile[kKnnTile];
+  const int b = blockIdx.y;
+  const int i = blockIdx.x * kKnnThreads + threadIdx.x;
+  const float *q = queries + (size_t)b * Nq * 3;
+  const float *r = refs + (size_t)b * Nr * 3;
+  float q0 = 0.f, q1 = 0.f, q2 = 0.f, qq = 0.f;
+  if (i < Nq) {
+    q0 = __ldg(q + (size_t)i * 3);
+    q1 = __ldg(q + (size_t)i * 3 + 1);
+    q2 = __ldg(q + (size_t)i * 3 + 2);
+    qq = hg_sumsq3_seq(q0, q1, q2);
+  }
+  const float n0 = -2.0f * q0, n1 = -2.0f * q1, n2 = -2.0f * q2;
+  TopK<KM> top;
+  top.init();
+  for (int base = 0; base < Nr; base += kKnnTile) {
+    __syncthreads();
+    for (int t = threadIdx.x; t < kKnnTile; t += kKnnThreads) {
+      const int j = base + t;
+      float4 v = make_float4(0.f, 0.f, 0.f, CUDART_INF_F);
+      if (j < Nr) {
+        v.x = __ldg(r + (size_t)j * 3);
+        v.y = __ldg(r + (size_t)j * 3 + 1);
+        v.z = __ldg(r + (size_t)j * 3 + 2);
+        v.w = (FORM == FORM_EXPANDED) ? hg_sumsq3_seq(v.x, v.y, v.z) : 0.f;
+      }
+      tile[t] = v;
+    }
+    __syncthreads();
+    const int lim = min(kKnnTile, Nr - base);
+#pragma unroll 4
+    for (int t = 0; t < lim; ++t) {
+      const float4 c = tile[t];
+      float d;
+      if (FORM == FORM_EXPANDED) {
+        const float nzz = __fmaf_rn(n2, c.z, __fmaf_rn(n1, c.y, __fmul_rn(n0, c.x)));  // == -2*zz exactly
+        d = __fadd_rn(__fadd_rn(c.w, nzz), qq);
+      } else {
+        d = hg_dist3_fma(q0, q1, q2, c.x, c.y, c.z);
+      }
+      top.push(d, base + t);
+    }
+  }
+  if (i < Nq) {
+#pragma unroll
+    for (int t = 0; t < KM; ++t) {
+      if (t < k1) {
+        if (vals) vals[((size_t)b * Nq + i) * k1 + t] = top.v[t];
+        idx[((size_t)b * Nq + i) * k1 + t] = (IdxT)top.id[t];
+      }
+    }
+  }
+}
+
+template <int FORM, typename IdxT>
+int launch_knn3(const float *q, const float *r, int B, int Nq, int Nr, int k1, float *vals, IdxT *idx,
+                cudaStream_t stream) {
+  dim3 grid((Nq + kKnnThreads - 1) / kKnnThreads, B);
+#define HG_KNN_CASE(KM)                                                                              \
+  if (k1 <= KM) {                                                                                    \
+    const bool prof = hg_prof_begin(HG_PROF_KNN, stream);                                            \
+    knn3_kernel<KM, FORM, IdxT><<<grid, kKnnThreads, 0, stream>>>(q, r, Nq, Nr, k1, vals, idx);      \
+    hg_prof_end(HG_PROF_KNN, stream, prof);                                                          \
+    HG_CHECK_LAUNCH("knn3_kernel");                                                                  \
+    return HG_OK;                                                                                    \
+  }
+  HG_KNN_CASE(4)
+  HG_KNN_CASE(6)
+  HG_KNN_CASE(8)
+  HG_KNN_CASE(12)
+  HG_KNN_CASE(17)
+  HG_KNN_CASE(20)
+  HG_KNN_CASE(24)
+  HG_KNN_CASE(32)
+#undef HG_KNN_CASE
+  hg_set_error("knn: k=%d > 32 unsupported", k1);
+  return HG_E_UNSUPPORTED;
+}
+
+// ---- generic channel count (DGCNN edge-conv layers 2-4: C = 64, 64, 128) ------------------------------------
+// xx with ATen's cascade-sum order (levels of 16): probed bit-exact for C = 64, 128.
+__global__ void knn_sumsq_kernel(const float *__restrict__ pc, long long total, int C, float *__restrict__ xx) {
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total;
+       g += (long long)gridDim.x * blockDim.x) {
+    const float *a = pc + (size_t)g * C;
+    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
+    for (int c = 0; c < C; ++c) {
+      acc0 = __fadd_rn(acc0, __fmul_rn(a[c], a[c]));
+      if (((c + 1) & 15) == 0) {
+        acc1 = __fadd_rn(acc1, acc0);
+        acc0 = 0.f;
+        if (((c + 1) & 255) == 0) {
+          acc2 = __fadd_rn(acc2, acc1);
+          acc1 = 0.f;
+        }
+      }
+    }
+    xx[g] = __fadd_rn(__fadd_rn(acc0, acc1), acc2);
+  }
+}
+
+// dist tile: 64x64 per CTA, 4x4 per thread, channels consumed strictly in order (sequential FMA chain).
+constexpr int kGT = 64, kGC = 16;
+__global__ void __launch_bounds__(256) knn_dist_generic_kernel(const float *__restrict__ pc,
+                                                               const float *__restrict__ xx, int K, int C,
+                                                               float *__restrict__ dist /*[nb,K,K]*/) {
+  __shared__ float As[kGC][kGT + 1], Bs[kGC][kGT + 1];
+  const int b = blockIdx.z;
+  const float *p = pc + (size_t)b * K * C;
+  const int i0 = blockIdx.y * kGT, j0 = blockIdx.x * kGT;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  float acc[4][4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+#pragma unroll
+    for (int v = 0; v < 4; ++v) acc[u][v] = 0.f;
+  for (int c0 = 0; c0 < C; c0 += kGC) {
+    __syncthreads();
+    for (int t = threadIdx.x; t < kGT * kGC; t += 256) {
+      const int rrow = t / kGC, cc = t % kGC;
+      const int c = c0 + cc;
+      As[cc][rrow] = (i0 + rrow < K && c < C) ? p[(size_t)(i0 + rrow) * C + c] : 0.f;
+      Bs[cc][rrow] = (j0 + rrow < K && c < C) ? p[(size_t)(j0 + rrow) * C + c] : 0.f;
+    }
+    __syncthreads();
+    const int cl = min(kGC, C - c0);
+    for (int cc = 0; cc < cl; ++cc) {
+      float a[4], bb[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) a[u] = As[cc][ty * 4 + u];
+#pragma unroll
+      for (int v = 0; v < 4; ++v) bb[v] = Bs[cc][tx * 4 + v];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) acc[u][v] = __fmaf_rn(a[u], bb[v], acc[u][v]);
+    }
+  }
+  const float *xb = xx + (size_t)b * K;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int i = i0 + ty * 4 + u;
+    if (i >= K) continue;
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      const int j = j0 + tx * 4 + v;
+      if (j >= K) continue;
+      dist[((size_t)b * K + i) * K + j] = __fadd_rn(__fadd_rn(xb[j], __fmul_rn(-2.0f, acc[u][v])), xb[i]);
+    }
+  }
+}
+
+// Warp per row: k1 rounds of "smallest (value, index) strictly after the previous pick".
+__global__ void __launch_bounds__(128) knn_select_rows_kernel(const float *__restrict__ dist, int nrows, int K,
+                                                              int k1, float *__restrict__ vals,
+                                                              int *__restrict__ idx) {
+  extern __shared__ float rowbuf[];  // [4 warps][K]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float *row = rowbuf + (size_t)warp * K;
+  for (int r = blockIdx.x * 4 + warp; r < nrows; r += gridDim.x * 4) {
+    __syncwarp();
+    for (int j = lane; j < K; j += 32) row[j] = dist[(size_t)r * K + j];
+    __syncwarp();
+    float pv = -CUDART_INF_F;
+    int pj = -1;
+    for (int t = 0; t < k1; ++t) {
+      float bv = CUDART_INF_F;
+      int bj = 0x7fffffff;
+      for (int j = lane; j < K; j += 32) {
+        const float v = row[j];
+        const bool after = (v > pv) || (v == pv && j > pj);
+        if (after && (v < bv)) {  // ascending j per lane: strict '<' keeps the lowest index
+          bv = v;
+          bj = j;
+        }
+      }
+      const float wv = hg_warp_min_f32(bv);
+      const int cand = (bv == wv) ? bj : 0x7fffffff;
+      const int wj = __reduce_min_sync(0xffffffffu, cand);
+      pv = wv;
+      pj = wj;
+      if (lane == 0) {
+        if (vals) vals[(size_t)r * k1 + t] = wv;
+        idx[(size_t)r * k1 + t] = wj;
+      }
+    }
+  }
+}
+
+// ---- kNN-outlier loss ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) knn_outlier_fwd_kernel(const float *__restrict__ vals, int K, int k1,
+                                                              float alpha, const float *__restrict__ weights,
+                                                              float *__restrict__ value, float *__restrict__ mask,
+                                                              float *__restrict__ loss) {
+  const int b = blockIdx.x, tid = threadIdx.x;
+  __shared__ double red[256];
+  __shared__ float thr_s;
+  const float *v = vals + (size_t)b * K * k1;
+  float *val = value + (size_t)b * K;
+  const float kf = (float)(k1 - 1);
+  double s = 0.0;
+  for (int i = tid; i < K; i += 256) {
+    float acc = v[(size_t)i * k1 + 1];
+    for (int t = 2; t < k1; ++t) acc = __fadd_rn(acc, v[(size_t)i * k1 + t]);
+    const float x = __fdiv_rn(acc, kf);
+    val[i] = x;
+    s += (double)x;
+  }
+  red[tid] = s;
+  __syncthreads();
+  for (int st = 128; st > 0; st >>= 1) {
+    if (tid < st) red[tid] += red[tid + st];
+    __syncthreads();
+  }
+  const double mean = red[0] / (double)K;
+  __syncthreads();
+  double ss = 0.0;
+  for (int i = tid; i < K; i += 256) {
+    const double d = (double)val[i] - mean;
+    ss += d * d;
+  }
+  red[tid] = ss;
+  __syncthreads();
+  for (int st = 128; st > 0; st >>= 1) {
+    if (tid < st) red[tid] += red[tid + st];
+    __syncthreads();
+  }
+  if (tid == 0) {
+    const float stdf = (float)sqrt(red[0] / (double)(K - 1));  // torch.std: unbiased
+    thr_s = __fadd_rn((float)mean, __fmul_rn(alpha, stdf));
+  }
+  __syncthreads();
+  const float thr = thr_s;
+  double l = 0.0;
+  for (int i = tid; i < K; i += 256) {
+    const float m = val[i] > thr ? 1.f : 0.f;
+    mask[(size_t)b * K + i] = m;
+    l += (double)__fmul_rn(val[i], m);
+  }
+  __syncthreads();
+  red[tid] = l;
+  __syncthreads();
+  for (int st = 128; st > 0; st >>= 1) {
+    if (tid < st) red[tid] += red[tid + st];
+    __syncthreads();
+  }
+  if (tid == 0) {
+    const float lb = (float)(red[0] / (double)K);
+    loss[b] = weights ? __fmul_rn(lb, weights[b]) : lb;
+  }
+}
+
+__global__ void knn_bwd_keys_kernel(const int *__restrict__ idx, const float *__restrict__ mask, long long total,
+                                    int k1, int *__restrict__ keys) {
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total;
+       g += (long long)gridDim.x * blockDim.x) {
+    const int t = (int)(g % k1);
+    const long long row = g / k1;
+    keys[g] = (t >= 1 && mask[row] != 0.f) ? idx[g] : -1;
+  }
+}
+
+// grad[n] = coef * ( [mask_n] sum_t 2(p_n - p_{idx[n,t]})  +  sum_{edges (i,t)->n, mask_i} 2(p_n - p_i) )
+__global__ void __launch_bounds__(256) knn_outlier_bwd_kernel(const float *__restrict__ pc,
+                                                              const int *__restrict__ idx,
+                                                              const float *__restrict__ mask,
+                                                              const float *__restrict__ g, const int *__restrict__ off,
+                                                              const int *__restrict__ list, int B, int K, int C, int k1,
+                                                              float *__restrict__ grad) {
+  const long long total = (long long)B * K;
+  for (long long gi = (long long)blockIdx.x * blockDim.x + threadIdx.x; gi < total;
+       gi += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(gi / K), n = (int)(gi % K);
+    const float *p = pc + (size_t)b * K * C;
+    const float coef = g[b] / ((float)K * (float)(k1 - 1));
+    const bool own = mask[gi] != 0.f;
+    const int *nb = idx + (size_t)gi * k1;
+    const int *o = off + (size_t)b * (K + 1);
+    const int *l = list + (size_t)b * K * k1;
+    const int p0 = o[n], p1 = o[n + 1];
+    for (int c = 0; c < C; ++c) {
+      const float v = p[(size_t)n * C + c];
+      float acc = 0.f;
+      if (own)
+        for (int t = 1; t < k1; ++t) acc += 2.0f * (v - p[(size_t)nb[t] * C + c]);
+      for (int q = p0; q < p1; ++q) acc += 2.0f * (v - p[(size_t)(l[q] / k1) * C + c]);
+      grad[(size_t)gi * C + c] = coef * acc;
+    }
+  }
+}
+
+int grid_for(long long total, int threads) {
+  long long blocks = (total + threads - 1) / threads;
+  const long long cap = (long long)hg_sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+constexpr size_t kGenericScratchBytes = (size_t)256 << 20;
+
+}  // namespace
+
+HG_API size_t hg_knn_self_workspace_bytes(int B, int K, int C, int k1) {
+  (void)k1;
+  if (B <= 0 || K <= 0 || C <= 0) return 0;
+  if (C == 3) return 256;
+  size_t per = (size_t)K * K * sizeof(float);
+  size_t nb = kGenericScratchBytes / per;
+  if (nb < 1) nb = 1;
+  if (nb > (size_t)B) nb = (size_t)B;
+  return hg_align((size_t)B * K * sizeof(float)) + hg_align(nb * per);
+}
+
+HG_API int hg_knn_self_f32(const float *pc, int B, int K, int C, int k1, float *vals, int *idx, void *workspace,
+                           size_t workspace_bytes, hgStream stream_) {
+  cudaStream_t stream = hg_stream(stream_);
+  HG_REQUIRE(pc && idx, HG_E_BADARG, "knn_self: null pointer");
+  HG_REQUIRE(B > 0 && K > 0 && C > 0, HG_E_BADARG, "knn_self: sizes must be positive");
+  HG_REQUIRE(k1 >= 1 && k1 <= 32 && k1 <= K, HG_E_BADARG, "knn_self: need 1 <= k <= min(32, K); got k=%d K=%d", k1, K);
+  HG_REQUIRE(B <= 65535, HG_E_UNSUPPORTED, "knn_self: B=%d > 65535 clouds per call", B);
+  if (C == 3) return launch_knn3<FORM_EXPANDED, int>(pc, pc, B, K, K, k1, vals, idx, stream);
+  const size_t need = hg_knn_self_workspace_bytes(B, K, C, k1);
+  HG_REQUIRE(workspace && workspace_bytes >= need, HG_E_WORKSPACE, "knn_self: workspace too small (%zu < %zu)",
+             workspace_bytes, need);
+  HG_REQUIRE((size_t)K * sizeof(float) * 4 <= 200 * 1024, HG_E_UNSUPPORTED, "knn_self: K=%d too large for C=%d path", K, C);
+  float *xx = (float *)workspace;
+  float *dist = (float *)((char *)workspace + hg_align((size_t)B * K * sizeof(float)));
+  knn_sumsq_kernel<<<grid_for((long long)B * K, 256), 256, 0, stream>>>(pc, (long long)B * K, C, xx);
+  HG_CHECK_LAUNCH("knn_sumsq_kernel");
+  const size_t per = (size_t)K * K * sizeof(float);
+  int nb = (int)(kGenericScratchBytes / per);
+  if (nb < 1) nb = 1;
+  const size_t sel_smem = (size_t)4 * K * sizeof(float);
+  if (sel_smem > 48 * 1024)
+    HG_CUDA(cudaFuncSetAttribute(knn_select_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem));
+  for (int b0 = 0; b0 < B; b0 += nb) {
+    const int cb = (B - b0 < nb) ? (B - b0) : nb;
+    dim3 grid((K + kGT - 1) / kGT, (K + kGT - 1) / kGT, cb);
+    knn_dist_generic_kernel<<<grid, 256, 0, stream>>>(pc + (size_t)b0 * K * C, xx + (size_t)b0 * K, K, C, dist);
+    HG_CHECK_LAUNCH("knn_dist_generic_kernel");
+    const int nrows = cb * K;
+    knn_select_rows_kernel<<<grid_for((long long)nrows * 32, 128), 128, sel_smem, stream>>>(
+        dist, nrows, K, k1, vals ? vals + (size_t)b0 * K * k1 : nullptr, idx + (size_t)b0 * K * k1);
+    HG_CHECK_LAUNCH("knn_select_rows_kernel");
+  }
+  return HG_OK;
+}
+
+HG_API int hg_knn_points_f32(const float *p1, const float *p2, int B, int N, int M, int K, float *dists, int64_t *idx,
+                             hgStream stream_) {
+  HG_REQUIRE(p1 && p2 && idx, HG_E_BADARG, "knn_points: null pointer");
+  HG_REQUIRE(B > 0 && N > 0 && M > 0, HG_E_BADARG, "knn_points: sizes must be positive");
+  HG_REQUIRE(K >= 1 && K <= 32 && K <= M, HG_E_BADARG, "knn_points: need 1 <= K <= min(32, M); got K=%d M=%d", K, M);
+  HG_REQUIRE(B <= 65535, HG_E_UNSUPPORTED, "knn_points: B=%d > 65535 clouds per call", B);
+  return launch_knn3<FORM_DIRECT, long long>(p1, p2, B, N, M, K, dists, (long long *)idx, hg_stream(stream_));
+}
+
+HG_API int hg_knn_outlier_fwd_f32(const float *vals, int B, int K, int k1, float alpha, const float *weights,
+                                  float *value, float *mask, float *loss, hgStream stream_) {
+  HG_REQUIRE(vals && value && mask && loss, HG_E_BADARG, "knn_outlier_fwd: null pointer");
+  HG_REQUIRE(B > 0 && K > 1 && k1 >= 2, HG_E_BADARG, "knn_outlier_fwd: need K > 1 and k >= 1");
+  knn_outlier_fwd_kernel<<<B, 256, 0, hg_stream(stream_)>>>(vals, K, k1, alpha, weights, value, mask, loss);
+  HG_CHECK_LAUNCH("knn_outlier_fwd_kernel");
+  return HG_OK;
+}
+
+HG_API size_t hg_knn_outlier_bwd_workspace_bytes(int B, int K, int k1) {
+  if (B <= 0 || K <= 0 || k1 <= 0) return 0;
+  return hg_align((size_t)B * K * k1 * sizeof(int)) + hg_csr_workspace_bytes(B, K, K * k1);
+}
+
+HG_API int hg_knn_outlier_bwd_f32(const float *pc, const int *idx, const float *mask, const float *g, int B, int K,
+                                  int C, int k1, float *grad_pc, void *workspace, size_t workspace_bytes,
+                                  hgStream stream_) {
+  cudaStream_t stream = hg_stream(stream_);
+  HG_REQUIRE(pc && idx && mask && g && grad_pc, HG_E_BADARG, "knn_outlier_bwd: null pointer");
+  HG_REQUIRE(B > 0 && K > 1 && C > 0 && k1 >= 2, HG_E_BADARG, "knn_outlier_bwd: bad sizes");
+  HG_REQUIRE(workspace && workspace_bytes >= hg_knn_outlier_bwd_workspace_bytes(B, K, k1), HG_E_WORKSPACE,
+             "knn_outlier_bwd: workspace too small");
+  int *keys = (int *)workspace;
+  void *csr_ws = (char *)workspace + hg_align((size_t)B * K * k1 * sizeof(int));
+  const long long total = (long long)B * K * k1;
+  knn_bwd_keys_kernel<<<grid_for(total, 256), 256, 0, stream>>>(idx, mask, total, k1, keys);
+  HG_CHECK_LAUNCH("knn_bwd_keys_kernel");
+  HgCsr csr;
+  int rc = hg_csr_build(keys, B, K * k1, K, csr_ws, hg_csr_workspace_bytes(B, K, K * k1), &csr, stream);
+  if (rc) return rc;
+  knn_outlier_bwd_kernel<<<grid_for((long long)B * K, 256), 256, 0, stream>>>(pc, idx, mask, g, csr.off, csr.list, B, K,
+                                                                              C, k1, grad_pc);
+  HG_CHECK_LAUNCH("knn_outlier_bwd_kernel");
+  return HG_OK;
+}

@@ -1,0 +1,562 @@
+// hg_nn_bidir.cu -- fused pairwise-distance + bidirectional nearest neighbour for Chamfer / Hausdorff.
+//
+// Replaces util/set_distance.py:15-32 (_Distance.batch_pairwise_dist: three torch.bmm that materialise
+// xx, yy, zz and P, each [B,N2,N1]) together with the two torch.min reductions of :45-48 / :65-68.
+// Nothing of size N2 x N1 is ever stored: HBM traffic is the two clouds in and (min,argmin) out.
+//
+// Arithmetic (bit-exact restatement of the reference's FP32 matrix, SURVEY.md section 8 a-bis):
+//     rx_i = fma(x2,x2, fma(x1,x1, x0*x0))         diag(bmm(x,x^T))
+//     zz   = fma(x2,y2, fma(x1,y1, x0*y0))         bmm(x,y^T)
+//     P    = (rx_i + ry_j) - 2*zz
+// computed as  P = (rx_i + ry_j) + zz',  zz' = fma(x2',y2, fma(x1',y1, x0'*y0)),  x' = -2x  (scaling by -2
+// commutes with every rounding, so zz' == -2*zz exactly).
+//
+// Kernel design for sm_100a.  The inner dimension is 3, so this is FP32-pipe work, not tensor-core work.
+// Per pair the FMA pipe must execute 5 operations (FMUL, 2 FFMA, 2 FADD); they are issued as packed
+// FMUL2/FFMA2/FADD2 (two pairs per instruction, scalar x-operand broadcast by the .F32 operand form), which
+// halves the issue slots and leaves room for the min bookkeeping on the ALU pipe:
+//   * a lane keeps T columns (preds) resident in registers and streams the rows (gts) of the CTA's row
+//     block from shared memory (one broadcast LDS.128 per row: -2x0,-2x1,-2x2,rx);
+//   * column direction (min over rows): FMNMX3 over two rows at a time into T running minima; which block
+//     of kColBatch rows produced the minimum is tracked every kColBatch rows;
+//   * row direction (min over columns): FMNMX3 tree over the lane's T values, one CREDUX.MIN.F32 across the
+//     warp, and a ballot that records WHICH lane attained it;
+//   * only minima are tracked in the loop ("two-level argmin"): the exact first index is recovered by the
+//     finish kernel, which re-evaluates the kColBatch rows / T columns named by the coarse id with the same
+//     arithmetic and takes the first exact match -- torch.min's first-index tie rule.
+// Partial results of different CTAs are merged with 64-bit integer atomicMin on (ordered value bits, coarse
+// id): order-independent, hence deterministic.
+#include "hg_common.cuh"
+
+namespace {
+
+constexpr int kColBatch = 8;  // rows per column-direction tracking batch (and rescan width)
+
+struct NnParams {
+  const float *gts;    // [B,N2,3]
+  const float *preds;  // [B,N1,3]
+  int N2, N1;
+  int RB;                       // rows per CTA (multiple of kColBatch)
+  unsigned long long *colres;   // [B,N1]  (ord(min over rows) << 32) | global row batch
+  unsigned long long *rowres;   // [B,N2]  (ord(min over cols) << 32) | (column group << 5 | lane)
+};
+
+// exact P for the finish kernel; identical operation sequence to the packed main loop
+__device__ __forceinline__ float nn_p_exact(float x0, float x1, float x2, float y0, float y1, float y2) {
+  const float rx = hg_dot3_fma(x0, x1, x2, x0, x1, x2);
+  const float ry = hg_dot3_fma(y0, y1, y2, y0, y1, y2);
+  const float t = __fmaf_rn(-2.0f * x2, y2, __fmaf_rn(-2.0f * x1, y1, __fmul_rn(-2.0f * x0, y0)));
+  return __fadd_rn(__fadd_rn(rx, ry), t);
+}
+
+template <int T, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) nn_bidir_d3_kernel(NnParams p) {
+  static_assert(T % 2 == 0, "columns are processed as packed pairs");
+  constexpr int TP = T / 2;
+  extern __shared__ float4 smem[];
+  float4 *xs = smem;                                            // [RB] (-2x0,-2x1,-2x2,rx)
+  uint4 *rowpart = reinterpret_cast<uint4 *>(smem + p.RB);      // [WARPS][RB/2] (m_a,mask_a,m_b,mask_b)
+
+  const int b = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cgroup = blockIdx.y * WARPS + warp;  // global column group (32*T columns)
+  const int cbase = cgroup * 32 * T + lane * T;
+  const int r0 = blockIdx.x * p.RB;
+  const bool warp_active = cgroup * 32 * T < p.N1;
+
+  // ---- stage the row block: (-2x, rx); rows past N2 get rx=+inf so they never win a minimum -----------------
+  const float *gx = p.gts + (size_t)b * p.N2 * 3;
+  for (int r = threadIdx.x; r < p.RB; r += WARPS * 32) {
+    const int i = r0 + r;
+    float4 v = make_float4(0.f, 0.f, 0.f, CUDART_INF_F);
+    if (i < p.N2) {
+      const float x0 = __ldg(gx + (size_t)i * 3), x1 = __ldg(gx + (size_t)i * 3 + 1), x2 = __ldg(gx + (size_t)i * 3 + 2);
+      v = make_float4(-2.0f * x0, -2.0f * x1, -2.0f * x2, hg_dot3_fma(x0, x1, x2, x0, x1, x2));
+    }
+    xs[r] = v;
+  }
+
+  // ---- this lane's T columns, packed in pairs; columns past N1 get ry=+inf ---------------------------------
+  float2 y0[TP], y1[TP], y2[TP], ry[TP];
+  const float *gy = p.preds + (size_t)b * p.N1 * 3;
+#pragma unroll
+  for (int q = 0; q < TP; ++q) {
+    float a[2][4];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int j = cbase + 2 * q + h;
+      a[h][0] = a[h][1] = a[h][2] = 0.f;
+      a[h][3] = CUDART_INF_F;
+      if (j < p.N1) {
+        a[h][0] = __ldg(gy + (size_t)j * 3);
+        a[h][1] = __ldg(gy + (size_t)j * 3 + 1);
+        a[h][2] = __ldg(gy + (size_t)j * 3 + 2);
+        a[h][3] = hg_dot3_fma(a[h][0], a[h][1], a[h][2], a[h][0], a[h][1], a[h][2]);
+      }
+    }
+    y0[q] = make_float2(a[0][0], a[1][0]);
+    y1[q] = make_float2(a[0][1], a[1][1]);
+    y2[q] = make_float2(a[0][2], a[1][2]);
+    ry[q] = make_float2(a[0][3], a[1][3]);
+  }
+  __syncthreads();
+
+  if (warp_active) {
+    float cm[T], prev[T];
+    int cid[T];
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      cm[t] = CUDART_INF_F;
+      prev[t] = CUDART_INF_F;
+      cid[t] = r0 / kColBatch;
+    }
+    uint4 *myrow = rowpart + (size_t)warp * (p.RB / 2);
+
+    for (int rb = 0; rb < p.RB; rb += kColBatch) {
+#pragma unroll
+      for (int rr = 0; rr < kColBatch; rr += 2) {
+        const float4 xa = xs[rb + rr], xb = xs[rb + rr + 1];
+        float2 pa[TP], pb[TP];
+#pragma unroll
+        for (int q = 0; q < TP; ++q) {
+          float2 ta = __fmul2_rn(make_float2(xa.x, xa.x), y0[q]);
+          float2 tb = __fmul2_rn(make_float2(xb.x, xb.x), y0[q]);
+          ta = __ffma2_rn(make_float2(xa.y, xa.y), y1[q], ta);
+          tb = __ffma2_rn(make_float2(xb.y, xb.y), y1[q], tb);
+          ta = __ffma2_rn(make_float2(xa.z, xa.z), y2[q], ta);
+          tb = __ffma2_rn(make_float2(xb.z, xb.z), y2[q], tb);
+          const float2 sa = __fadd2_rn(make_float2(xa.w, xa.w), ry[q]);
+          const float2 sb = __fadd2_rn(make_float2(xb.w, xb.w), ry[q]);
+          pa[q] = __fadd2_rn(sa, ta);
+          pb[q] = __fadd2_rn(sb, tb);
+          cm[2 * q] = fminf(fminf(cm[2 * q], pa[q].x), pb[q].x);
+          cm[2 * q + 1] = fminf(fminf(cm[2 * q + 1], pa[q].y), pb[q].y);
+        }
+        float ma = fminf(pa[0].x, pa[0].y), mb = fminf(pb[0].x, pb[0].y);
+#pragma unroll
+        for (int q = 1; q < TP; ++q) {
+          ma = fminf(fminf(ma, pa[q].x), pa[q].y);
+          mb = fminf(fminf(mb, pb[q].x), pb[q].y);
+        }
+        const float wa = hg_warp_min_f32(ma), wb = hg_warp_min_f32(mb);
+        const unsigned ka = __ballot_sync(0xffffffffu, ma == wa);
+        const unsigned kb = __ballot_sync(0xffffffffu, mb == wb);
+        if (lane == 0) myrow[(rb + rr) >> 1] = make_uint4(__float_as_uint(wa), ka, __float_as_uint(wb), kb);
+      }
+      const int batch = (r0 + rb) / kColBatch;
+#pragma unroll
+      for (int t = 0; t < T; ++t) {
+        if (cm[t] < prev[t]) cid[t] = batch;
+        prev[t] = cm[t];
+      }
+    }
+    // column direction: merge with the other row blocks
+    unsigned long long *cr = p.colres + (size_t)b * p.N1;
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      const int j = cbase + t;
+      if (j < p.N1) atomicMin(cr + j, ((unsigned long long)hg_ord(cm[t]) << 32) | (unsigned)cid[t]);
+    }
+  }
+  __syncthreads();
+
+  // row direction: merge the CTA's warps (lowest warp = lowest columns wins ties), then the other CTAs
+  unsigned long long *rr_out = p.rowres + (size_t)b * p.N2;
+  for (int r = threadIdx.x; r < p.RB; r += WARPS * 32) {
+    const int i = r0 + r;
+    if (i >= p.N2) continue;
+    float best = CUDART_INF_F;
+    unsigned code = 0xffffffffu;
+    for (int w = 0; w < WARPS; ++w) {
+      if ((blockIdx.y * WARPS + w) * 32 * T >= p.N1) break;
+      const uint4 v = rowpart[(size_t)w * (p.RB / 2) + (r >> 1)];
+      const float m = __uint_as_float((r & 1) ? v.z : v.x);
+      const unsigned mask = (r & 1) ? v.w : v.y;
+      const unsigned c = ((unsigned)(blockIdx.y * WARPS + w) << 5) | (unsigned)(__ffs(mask) - 1);
+      if (m < best || code == 0xffffffffu) {
+        best = m;
+        code = c;
+      }
+    }
+    atomicMin(rr_out + i, ((unsigned long long)hg_ord(best) << 32) | code);
+  }
+}
+
+// Exact first-index recovery (torch.min tie rule) + unpacking of the merged results.
+template <int T>
+__global__ void __launch_bounds__(256) nn_bidir_d3_finish_kernel(NnParams p, int B, float *__restrict__ min1,
+                                                                  int *__restrict__ arg1, float *__restrict__ min2,
+                                                                  int *__restrict__ arg2) {
+  const long long total = (long long)B * (p.N1 + p.N2);
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total;
+       g += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(g / (p.N1 + p.N2));
+    const int e = (int)(g % (p.N1 + p.N2));
+    const float *gx = p.gts + (size_t)b * p.N2 * 3;
+    const float *gy = p.preds + (size_t)b * p.N1 * 3;
+    if (e < p.N1) {  // column j: nearest row inside the recorded batch of kColBatch rows
+      const int j = e;
+      const unsigned long long key = p.colres[(size_t)b * p.N1 + j];
+      const float m = hg_unord((unsigned)(key >> 32));
+      const int i0 = (int)(unsigned)(key & 0xffffffffu) * kColBatch;
+      const float y0 = __ldg(gy + (size_t)j * 3), y1 = __ldg(gy + (size_t)j * 3 + 1), y2 = __ldg(gy + (size_t)j * 3 + 2);
+      int arg = 0;
+      bool found = false;
+#pragma unroll
+      for (int d = 0; d < kColBatch; ++d) {
+        const int i = i0 + d;
+        if (i < p.N2 && !found) {
+          const float v = nn_p_exact(__ldg(gx + (size_t)i * 3), __ldg(gx + (size_t)i * 3 + 1),
+                                     __ldg(gx + (size_t)i * 3 + 2), y0, y1, y2);
+          if (v == m) {
+            arg = i;
+            found = true;
+          }
+        }
+      }
+      min1[(size_t)b * p.N1 + j] = m;
+      arg1[(size_t)b * p.N1 + j] = arg;
+    } else {  // row i: nearest column among the T columns of the recorded lane
+      const int i = e - p.N1;
+      const unsigned long long key = p.rowres[(size_t)b * p.N2 + i];
+      const float m = hg_unord((unsigned)(key >> 32));
+      const unsigned code = (unsigned)(key & 0xffffffffu);
+      const int j0 = (int)(code >> 5) * 32 * T + (int)(code & 31u) * T;
+      const float x0 = __ldg(gx + (size_t)i * 3), x1 = __ldg(gx + (size_t)i * 3 + 1), x2 = __ldg(gx + (size_t)i * 3 + 2);
+      int arg = 0;
+      bool found = false;
+#pragma unroll
+      for (int d = 0; d < T; ++d) {
+        const int j = j0 + d;
+        if (j < p.N1 && !found) {
+          const float v = nn_p_exact(x0, x1, x2, __ldg(gy + (size_t)j * 3), __ldg(gy + (size_t)j * 3 + 1),
+                                     __ldg(gy + (size_t)j * 3 + 2));
+          if (v == m) {
+            arg = j;
+            found = true;
+          }
+        }
+      }
+      min2[(size_t)b * p.N2 + i] = m;
+      arg2[(size_t)b * p.N2 + i] = arg;
+    }
+  }
+}
+
+// ---- generic inner dimension (R3: HiT_ADV.py:229-231 feeds [B,3,K], i.e. N=3 "points" of dimension K) ------
+// One thread per matrix entry, sequential FMA chain over D (the order the oracle uses).  Small problems only.
+__global__ void nn_generic_p_kernel(const float *__restrict__ gts, const float *__restrict__ preds, int B, int N2,
+                                    int N1, int D, float *__restrict__ P) {
+  const long long total = (long long)B * N2 * N1;
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total;
+       g += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(g % N1);
+    const int i = (int)((g / N1) % N2);
+    const int b = (int)(g / ((long long)N1 * N2));
+    const float *x = gts + ((size_t)b * N2 + i) * D;
+    const float *y = preds + ((size_t)b * N1 + j) * D;
+    float rx = __fmul_rn(x[0], x[0]), ry = __fmul_rn(y[0], y[0]), zz = __fmul_rn(x[0], y[0]);
+    for (int c = 1; c < D; ++c) {
+      const float xc = x[c], yc = y[c];
+      rx = __fmaf_rn(xc, xc, rx);
+      ry = __fmaf_rn(yc, yc, ry);
+      zz = __fmaf_rn(xc, yc, zz);
+    }
+    P[g] = __fsub_rn(__fadd_rn(rx, ry), __fmul_rn(2.0f, zz));
+  }
+}
+
+__global__ void nn_generic_min_kernel(const float *__restrict__ P, int B, int N2, int N1, float *__restrict__ min1,
+                                      int *__restrict__ arg1, float *__restrict__ min2, int *__restrict__ arg2) {
+  const long long total = (long long)B * (N1 + N2);
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total;
+       g += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(g / (N1 + N2));
+    const int e = (int)(g % (N1 + N2));
+    const float *Pb = P + (size_t)b * N2 * N1;
+    float best = CUDART_INF_F;
+    int arg = 0;
+    if (e < N1) {
+      for (int i = 0; i < N2; ++i) {
+        const float v = Pb[(size_t)i * N1 + e];
+        if (v < best) {
+          best = v;
+          arg = i;
+        }
+      }
+      min1[(size_t)b * N1 + e] = best;
+      arg1[(size_t)b * N1 + e] = arg;
+    } else {
+      const int i = e - N1;
+      for (int j = 0; j < N1; ++j) {
+        const float v = Pb[(size_t)i * N1 + j];
+        if (v < best) {
+          best = v;
+          arg = j;
+        }
+      }
+      min2[(size_t)b * N2 + i] = best;
+      arg2[(size_t)b * N2 + i] = arg;
+    }
+  }
+}
+
+// ---- Chamfer mean / Hausdorff max over the mins (set_distance.py:46-49, :66-69) -----------------------------
+// One CTA per (cloud, direction); fixed-order tree => deterministic.
+__global__ void __launch_bounds__(256) set_loss_kernel(const float *__restrict__ min1, const float *__restrict__ min2,
+                                                       int N1, int N2, int mode, float *__restrict__ loss1,
+                                                       float *__restrict__ loss2, int *__restrict__ hd_arg1,
+                                                       int *__restrict__ hd_arg2) {
+  const int b = blockIdx.x, dir = blockIdx.y;
+  const int N = dir ? N2 : N1;
+  const float *m = (dir ? min2 : min1) + (size_t)b * N;
+  __shared__ double sh_sum[256];
+  __shared__ float sh_val[256];
+  __shared__ int sh_idx[256];
+  const int tid = threadIdx.x;
+  if (mode == HG_MODE_CHAMFER) {
+    double s = 0.0;
+    for (int i = tid; i < N; i += 256) s += (double)m[i];
+    sh_sum[tid] = s;
+    __syncthreads();
+    for (int st = 128; st > 0; st >>= 1) {
+      if (tid < st) sh_sum[tid] += sh_sum[tid + st];
+      __syncthreads();
+    }
+    if (tid == 0) (dir ? loss2 : loss1)[b] = (float)(sh_sum[0] / (double)N);
+  } else {
+    float v = -CUDART_INF_F;
+    int a = 0x7fffffff;
+    for (int i = tid; i < N; i += 256) {
+      const float x = m[i];
+      if (x > v) {  // ascending i per thread: strict '>' keeps the first
+        v = x;
+        a = i;
+      }
+    }
+    sh_val[tid] = v;
+    sh_idx[tid] = a;
+    __syncthreads();
+    for (int st = 128; st > 0; st >>= 1) {
+      if (tid < st) {
+        const float v2 = sh_val[tid + st];
+        const int a2 = sh_idx[tid + st];
+        if (v2 > sh_val[tid] || (v2 == sh_val[tid] && a2 < sh_idx[tid])) {
+          sh_val[tid] = v2;
+          sh_idx[tid] = a2;
+        }
+      }
+      __syncthreads();
+    }
+    if (tid == 0) {
+      (dir ? loss2 : loss1)[b] = sh_val[0];
+      int *ha = dir ? hd_arg2 : hd_arg1;
+      if (ha) ha[b] = sh_idx[0] == 0x7fffffff ? 0 : sh_idx[0];
+    }
+  }
+}
+
+// ---- backward ---------------------------------------------------------------------------------------------
+// dP[i,j]/dy_j = 2(y_j - x_i), dP[i,j]/dx_i = 2(x_i - y_j).
+//   chamfer:  grad_y[j] = (g1/N1) 2(y_j - x_{arg1[j]})  +  (g2/N2) sum_{i: arg2[i]==j} 2(y_j - x_i)
+//             grad_x[i] = (g2/N2) 2(x_i - y_{arg2[i]})  +  (g1/N1) sum_{j: arg1[j]==i} 2(x_i - y_j)
+//   hausdorff: the same with one-hot row weights (only the arg-max pair of each direction).
+// The sums run over the reverse map in ascending source index: deterministic, no float atomics.
+__global__ void __launch_bounds__(256) set_loss_bwd_kernel(
+    const float *__restrict__ self_pts /*[B,Ns,D] points receiving the gradient*/,
+    const float *__restrict__ other_pts /*[B,No,D]*/, const int *__restrict__ self_arg /*[B,Ns] -> other*/,
+    const int *__restrict__ rev_off /*[B,Ns+1]*/, const int *__restrict__ rev_list /*[B,No] other idx, ascending*/,
+    const float *__restrict__ g_self /*[B] upstream of the loss that gathers (self -> nearest other)*/,
+    const float *__restrict__ g_other /*[B] upstream of the loss that scatters into self*/,
+    const int *__restrict__ hd_self /*[B] or null*/, const int *__restrict__ hd_other /*[B] or null*/, int B, int Ns,
+    int No, int D, int mode, float *__restrict__ grad_self) {
+  const long long total = (long long)B * Ns;
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total;
+       g += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(g / Ns), s = (int)(g % Ns);
+    const float *ps = self_pts + ((size_t)b * Ns + s) * D;
+    const float *po = other_pts + (size_t)b * No * D;
+    float cs, co;
+    if (mode == HG_MODE_CHAMFER) {
+      cs = g_self[b] / (float)Ns;
+      co = g_other[b] / (float)No;
+    } else {
+      cs = (hd_self[b] == s) ? g_self[b] : 0.f;
+      co = g_other[b];
+    }
+    const int a = self_arg[(size_t)b * Ns + s];
+    const int *off = rev_off + (size_t)b * (Ns + 1);
+    const int *lst = rev_list + (size_t)b * No;
+    const int p0 = off[s], p1 = off[s + 1];
+    const int hdo = (mode == HG_MODE_CHAMFER) ? -1 : hd_other[b];
+    for (int c = 0; c < D; ++c) {
+      const float v = ps[c];
+      float acc = 0.f;
+      if (cs != 0.f) acc = cs * (2.0f * (v - po[(size_t)a * D + c]));
+      float sc = 0.f;
+      for (int q = p0; q < p1; ++q) {
+        const int o = lst[q];
+        if (mode == HG_MODE_CHAMFER || o == hdo) sc += 2.0f * (v - po[(size_t)o * D + c]);
+      }
+      grad_self[((size_t)b * Ns + s) * D + c] = acc + co * sc;
+    }
+  }
+}
+
+template <int T, int WARPS>
+int launch_main(const NnParams &p, int B, cudaStream_t stream) {
+  const int ncg = (p.N1 + 32 * T - 1) / (32 * T);
+  dim3 grid((p.N2 + p.RB - 1) / p.RB, (ncg + WARPS - 1) / WARPS, B);
+  const size_t smem = (size_t)p.RB * sizeof(float4) + (size_t)WARPS * (p.RB / 2) * sizeof(uint4);
+  const bool prof = hg_prof_begin(HG_PROF_NN_BIDIR, stream);
+  nn_bidir_d3_kernel<T, WARPS><<<grid, WARPS * 32, smem, stream>>>(p);
+  hg_prof_end(HG_PROF_NN_BIDIR, stream, prof);
+  HG_CHECK_LAUNCH("nn_bidir_d3_kernel");
+  return HG_OK;
+}
+
+int grid_for(long long total, int threads) {
+  long long blocks = (total + threads - 1) / threads;
+  const long long cap = (long long)hg_sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+}  // namespace
+
+// Tunables exposed for the benchmark sweep (not part of the stable ABI): T (columns per lane: 8 or 16) and
+// rows per CTA.  0 = automatic.
+static int g_force_T = 0, g_force_RB = 0;
+HG_API void hg_nn_bidir_tune(int T, int RB) {
+  g_force_T = T;
+  g_force_RB = RB;
+}
+
+HG_API size_t hg_nn_bidir_workspace_bytes(int B, int N2, int N1, int D) {
+  if (B <= 0 || N1 <= 0 || N2 <= 0 || D <= 0) return 0;
+  if (D == 3) return hg_align((size_t)B * N1 * 8) + hg_align((size_t)B * N2 * 8);
+  return hg_align((size_t)B * N2 * N1 * sizeof(float));
+}
+
+HG_API int hg_nn_bidir_f32(const float *gts, const float *preds, int B, int N2, int N1, int D, float *min1, int *arg1,
+                           float *min2, int *arg2, void *workspace, size_t workspace_bytes, hgStream stream_) {
+  cudaStream_t stream = hg_stream(stream_);
+  HG_REQUIRE(gts && preds && min1 && arg1 && min2 && arg2, HG_E_BADARG, "nn_bidir: null pointer");
+  HG_REQUIRE(B > 0 && N1 > 0 && N2 > 0 && D > 0, HG_E_BADARG, "nn_bidir: sizes must be positive (B=%d N2=%d N1=%d D=%d)",
+             B, N2, N1, D);
+  HG_REQUIRE(B <= 65535, HG_E_UNSUPPORTED, "nn_bidir: B=%d > 65535 clouds per call", B);
+  const size_t need = hg_nn_bidir_workspace_bytes(B, N2, N1, D);
+  HG_REQUIRE(workspace && workspace_bytes >= need, HG_E_WORKSPACE, "nn_bidir: workspace too small (%zu < %zu)",
+             workspace_bytes, need);
+  if (D != 3) {
+    HG_REQUIRE((double)B * N2 * N1 <= 2.0e9, HG_E_UNSUPPORTED,
+               "nn_bidir: generic-D path materialises P; B*N2*N1 too large");
+    float *P = (float *)workspace;
+    const long long total = (long long)B * N2 * N1;
+    nn_generic_p_kernel<<<grid_for(total, 256), 256, 0, stream>>>(gts, preds, B, N2, N1, D, P);
+    HG_CHECK_LAUNCH("nn_generic_p_kernel");
+    nn_generic_min_kernel<<<grid_for((long long)B * (N1 + N2), 128), 128, 0, stream>>>(P, B, N2, N1, min1, arg1, min2,
+                                                                                         arg2);
+    HG_CHECK_LAUNCH("nn_generic_min_kernel");
+    return HG_OK;
+  }
+  NnParams p;
+  p.gts = gts;
+  p.preds = preds;
+  p.N2 = N2;
+  p.N1 = N1;
+  p.colres = (unsigned long long *)workspace;
+  p.rowres = (unsigned long long *)((char *)workspace + hg_align((size_t)B * N1 * 8));
+  HG_CUDA(cudaMemsetAsync(workspace, 0xff, need, stream));
+
+  int T = g_force_T ? g_force_T : (N1 > 256 ? 16 : 8);
+  // rows per CTA: enough CTAs to fill the machine several times over, but amortise the column load
+  int RB = g_force_RB;
+  if (!RB) {
+    RB = 64;
+    const long long ctas_at_64 = (long long)B * ((N2 + 63) / 64) * ((N1 + 32 * T * 2 - 1) / (32 * T * 2));
+    if (ctas_at_64 > (long long)hg_sm_count() * 64 && N2 >= 1024) RB = 128;
+  }
+  RB = (RB + kColBatch - 1) / kColBatch * kColBatch;
+  if (RB > 1024) RB = 1024;
+  p.RB = RB;
+  const int ncg = (N1 + 32 * T - 1) / (32 * T);
+  int rc;
+  if (T == 16) {
+    rc = (ncg >= 4 && ncg % 4 == 0) ? launch_main<16, 4>(p, B, stream)
+         : (ncg >= 2)               ? launch_main<16, 2>(p, B, stream)
+                                    : launch_main<16, 1>(p, B, stream);
+  } else {
+    T = 8;
+    rc = (ncg >= 4 && ncg % 4 == 0) ? launch_main<8, 4>(p, B, stream)
+         : (ncg >= 2)               ? launch_main<8, 2>(p, B, stream)
+                                    : launch_main<8, 1>(p, B, stream);
+  }
+  if (rc) return rc;
+  const long long total = (long long)B * (N1 + N2);
+  if (T == 16)
+    nn_bidir_d3_finish_kernel<16><<<grid_for(total, 256), 256, 0, stream>>>(p, B, min1, arg1, min2, arg2);
+  else
+    nn_bidir_d3_finish_kernel<8><<<grid_for(total, 256), 256, 0, stream>>>(p, B, min1, arg1, min2, arg2);
+  HG_CHECK_LAUNCH("nn_bidir_d3_finish_kernel");
+  return HG_OK;
+}
+
+HG_API int hg_pairwise_dist_f32(const float *x, const float *y, int B, int Nx, int Ny, int D, float *P,
+                                hgStream stream_) {
+  HG_REQUIRE(x && y && P, HG_E_BADARG, "pairwise_dist: null pointer");
+  HG_REQUIRE(B > 0 && Nx > 0 && Ny > 0 && D > 0, HG_E_BADARG, "pairwise_dist: sizes must be positive");
+  const long long total = (long long)B * Nx * Ny;
+  nn_generic_p_kernel<<<grid_for(total, 256), 256, 0, hg_stream(stream_)>>>(x, y, B, Nx, Ny, D, P);
+  HG_CHECK_LAUNCH("nn_generic_p_kernel");
+  return HG_OK;
+}
+
+HG_API int hg_set_loss_f32(const float *min1, const float *min2, int B, int N1, int N2, int mode, float *loss1,
+                           float *loss2, int *hd_arg1, int *hd_arg2, hgStream stream_) {
+  HG_REQUIRE(min1 && min2 && loss1 && loss2, HG_E_BADARG, "set_loss: null pointer");
+  HG_REQUIRE(B > 0 && N1 > 0 && N2 > 0, HG_E_BADARG, "set_loss: sizes must be positive");
+  HG_REQUIRE(mode == HG_MODE_CHAMFER || mode == HG_MODE_HAUSDORFF, HG_E_BADARG, "set_loss: bad mode %d", mode);
+  set_loss_kernel<<<dim3(B, 2), 256, 0, hg_stream(stream_)>>>(min1, min2, N1, N2, mode, loss1, loss2, hd_arg1, hd_arg2);
+  HG_CHECK_LAUNCH("set_loss_kernel");
+  return HG_OK;
+}
+
+HG_API size_t hg_set_loss_bwd_workspace_bytes(int B, int N2, int N1) {
+  if (B <= 0 || N1 <= 0 || N2 <= 0) return 0;
+  // reverse map of arg2 (N2 edges -> N1 keys) and of arg1 (N1 edges -> N2 keys)
+  return hg_csr_workspace_bytes(B, N1, N2) + hg_csr_workspace_bytes(B, N2, N1);
+}
+
+HG_API int hg_set_loss_bwd_f32(const float *gts, const float *preds, const int *arg1, const int *arg2,
+                               const int *hd_arg1, const int *hd_arg2, const float *g1, const float *g2, int B, int N2,
+                               int N1, int D, int mode, float *grad_preds, float *grad_gts, void *workspace,
+                               size_t workspace_bytes, hgStream stream_) {
+  cudaStream_t stream = hg_stream(stream_);
+  HG_REQUIRE(gts && preds && arg1 && arg2 && g1 && g2 && grad_preds, HG_E_BADARG, "set_loss_bwd: null pointer");
+  HG_REQUIRE(B > 0 && N1 > 0 && N2 > 0 && D > 0, HG_E_BADARG, "set_loss_bwd: sizes must be positive");
+  HG_REQUIRE(mode == HG_MODE_CHAMFER || (mode == HG_MODE_HAUSDORFF && hd_arg1 && hd_arg2), HG_E_BADARG,
+             "set_loss_bwd: bad mode / missing hausdorff arg-max indices");
+  HG_REQUIRE(workspace && workspace_bytes >= hg_set_loss_bwd_workspace_bytes(B, N2, N1), HG_E_WORKSPACE,
+             "set_loss_bwd: workspace too small");
+  // preds (adv, "y"): gathers through arg1 (loss1), receives scatter from arg2 (loss2)
+  HgCsr rev2;
+  int rc = hg_csr_build(arg2, B, N2, N1, workspace, hg_csr_workspace_bytes(B, N1, N2), &rev2, stream);
+  if (rc) return rc;
+  const long long tp = (long long)B * N1;
+  set_loss_bwd_kernel<<<grid_for(tp, 256), 256, 0, stream>>>(preds, gts, arg1, rev2.off, rev2.list, g1, g2, hd_arg1,
+                                                             hd_arg2, B, N1, N2, D, mode, grad_preds);
+  HG_CHECK_LAUNCH("set_loss_bwd_kernel(preds)");
+  if (grad_gts) {
+    HgCsr rev1;
+    void *ws2 = (char *)workspace + hg_csr_workspace_bytes(B, N1, N2);
+    rc = hg_csr_build(arg1, B, N1, N2, ws2, hg_csr_workspace_bytes(B, N2, N1), &rev1, stream);
+    if (rc) return rc;
+    const long long tg = (long long)B * N2;
+    set_loss_bwd_kernel<<<grid_for(tg, 256), 256, 0, stream>>>(gts, preds, arg2, rev1.off, rev1.list, g2, g1, hd_arg2,
+                                                               hd_arg1, B, N2, N1, D, mode, grad_gts);
+    HG_CHECK_LAUNCH("set_loss_bwd_kernel(gts)");
+  }
+  return HG_OK;
+}

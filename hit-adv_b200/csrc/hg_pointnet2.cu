@@ -1,0 +1,436 @@
+// hg_pointnet2.cu -- the nine pointnet2_ops kernels (pointnet2_ops_lib/pointnet2_ops/_ext-src/src/*.cu),
+// rewritten for sm_100a behind the reference's own C-style wrapper signatures, and the torch-level FPS of
+// model/pointnet2_utils.py:63-84 (same kernel, different arithmetic / tie rule).
+//
+// What changes w.r.t. the reference kernels (which launch ONE CTA per batch element, <= b of 148 SMs busy):
+//   * gather / group / interpolate: one thread per output element over the whole grid, coalesced stores;
+//   * *_grad: deterministic segmented sums over a reverse map (hg_csr.cu) instead of float atomicAdd;
+//   * ball query: a warp per centre scanning 32 points per step (ballot + prefix popcount keep the
+//     ascending-index order of the serial reference loop), early exit once nsample hits are found;
+//   * FPS: the cloud and the running distances live in registers for the whole launch, one 64-bit
+//     (distance, tie-key) max per round, ONE barrier per round (double-buffered warp results) instead of the
+//     reference's 10; the tie key reproduces the reference's shared-memory tree order exactly.
+// Index results are bit-identical to the reference kernels (same FMA contraction as nvcc emits for them).
+#include "hg_common.cuh"
+
+namespace {
+
+int grid_for(long long total, int threads) {
+  long long blocks = (total + threads - 1) / threads;
+  const long long cap = (long long)hg_sm_count() * 32;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+// cuda_utils.h:13-17 opt_n_threads -- only its value matters here: it fixes the reference FPS tie order.
+int ref_opt_n_threads(int work_size) {
+  const int pow_2 = (int)(std::log((double)work_size) / std::log(2.0));
+  int t = 1 << pow_2;
+  if (t > 512) t = 512;
+  if (t < 1) t = 1;
+  return t;
+}
+
+// ---- gather / group (sampling_gpu.cu:8-20, group_points_gpu.cu:8-28) ---------------------------------------
+// out[b,c,e] = points[b,c,idx[b,e]],  e over the flattened index tensor (m, or npoints*nsample)
+__global__ void __launch_bounds__(256) gather_channel_major_kernel(const float *__restrict__ points,
+                                                                   const int *__restrict__ idx, int b, int c, int n,
+                                                                   int E, float *__restrict__ out) {
+  const long long total = (long long)b * c * E;
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total;
+       g += (long long)gridDim.x * blockDim.x) {
+    const int e = (int)(g % E);
+    const long long bc = g / E;
+    const int bi = (int)(bc / c);
+    const int a = __ldg(idx + (size_t)bi * E + e);
+    out[g] = __ldg(points + (size_t)bc * n + a);
+  }
+}
+
+// grad_points[b,c,key] = sum over the edges e of key, ascending e, of src[b,c,e / DIV] * (w ? w[b,e] : 1)
+template <int DIV, bool WEIGHTED>
+__global__ void __launch_bounds__(256) scatter_channel_major_kernel(const float *__restrict__ src,
+                                                                    const float *__restrict__ w,
+                                                                    const int *__restrict__ off,
+                                                                    const int *__restrict__ list, int b, int c, int n,
+                                                                    int E, float *__restrict__ grad_points) {
+  const long long total = (long long)b * c * n;
+  const int Esrc = E / DIV;
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total;
+       g += (long long)gridDim.x * blockDim.x) {
+    const int key = (int)(g % n);
+    const long long bc = g / n;
+    const int bi = (int)(bc / c);
+    const int *o = off + (size_t)bi * (n + 1);
+    const int *l = list + (size_t)bi * E;
+    const float *s = src + (size_t)bc * Esrc;
+    float acc = 0.f;
+    for (int q = o[key]; q < o[key + 1]; ++q) {
+      const int e = l[q];
+      float v = s[e / DIV];
+      if (WEIGHTED) v = __fmul_rn(v, w[(size_t)bi * E + e]);
+      acc = __fadd_rn(acc, v);
+    }
+    grad_points[g] = acc;
+  }
+}
+
+// ---- ball query (ball_query_gpu.cu:9-44) -------------------------------------------------------------------
+__global__ void __launch_bounds__(128) ball_query_kernel(int n, int m, float radius2, int nsample,
+                                                         const float *__restrict__ new_xyz,
+                                                         const float *__restrict__ xyz, int *__restrict__ idx) {
+  const int b = blockIdx.y, lane = threadIdx.x & 31;
+  const int j = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (j >= m) return;
+  const float *p = xyz + (size_t)b * n * 3;
+  const float *q = new_xyz + ((size_t)b * m + j) * 3;
+  int *o = idx + ((size_t)b * m + j) * nsample;
+  const float cx = __ldg(q), cy = __ldg(q + 1), cz = __ldg(q + 2);
+  int cnt = 0, first = 0;
+  for (int k0 = 0; k0 < n && cnt < nsample; k0 += 32) {
+    const int k = k0 + lane;
+    bool hit = false;
+    if (k < n) {
+      const float d2 = hg_dist3_fma(cx, cy, cz, __ldg(p + (size_t)k * 3), __ldg(p + (size_t)k * 3 + 1),
+                                    __ldg(p + (size_t)k * 3 + 2));
+      hit = d2 < radius2;
+    }
+    const unsigned mask = __ballot_sync(0xffffffffu, hit);
+    if (mask) {
+      if (cnt == 0) first = k0 + __ffs(mask) - 1;
+      const int pos = cnt + __popc(mask & ((1u << lane) - 1u));
+      if (hit && pos < nsample) o[pos] = k;
+      cnt += __popc(mask);
+    }
+  }
+  if (cnt > nsample) cnt = nsample;
+  const int fill = (cnt == 0) ? 0 : first;  // no hit: the reference leaves its zero-initialised row
+  for (int l = cnt + lane; l < nsample; l += 32) o[l] = fill;
+}
+
+// ---- three_nn (interpolate_gpu.cu:9-59) ---------------------------------------------------------------------
+__global__ void __launch_bounds__(128) three_nn_kernel(int n, int m, const float *__restrict__ unknown,
+                                                       const float *__restrict__ known, float *__restrict__ dist2,
+                                                       int *__restrict__ idx) {
+  __shared__ float kx[512], ky[512], kz[512];
+  const int b = blockIdx.y;
+  const int j = blockIdx.x * 128 + threadIdx.x;
+  const float *u = unknown + (size_t)b * n * 3;
+  const float *kn = known + (size_t)b * m * 3;
+  float ux = 0.f, uy = 0.f, uz = 0.f;
+  if (j < n) {
+    ux = __ldg(u + (size_t)j * 3);
+    uy = __ldg(u + (size_t)j * 3 + 1);
+    uz = __ldg(u + (size_t)j * 3 + 2);
+  }
+  // the reference keeps its running bests in double initialised to 1e40; d is a float, so comparisons are
+  // the float comparisons below and an unfilled slot converts to +inf on output
+  float b1 = CUDART_INF_F, b2 = CUDART_INF_F, b3 = CUDART_INF_F;
+  int i1 = 0, i2 = 0, i3 = 0;
+  for (int base = 0; base < m; base += 512) {
+    __syncthreads();
+    for (int t = threadIdx.x; t < 512 && base + t < m; t += 128) {
+      kx[t] = __ldg(kn + (size_t)(base + t) * 3);
+      ky[t] = __ldg(kn + (size_t)(base + t) * 3 + 1);
+      kz[t] = __ldg(kn + (size_t)(base + t) * 3 + 2);
+    }
+    __syncthreads();
+    const int lim = min(512, m - base);
+    for (int t = 0; t < lim; ++t) {
+      const float d = hg_dist3_fma(ux, uy, uz, kx[t], ky[t], kz[t]);
+      const int k = base + t;
+      if (d < b1) {
+        b3 = b2; i3 = i2;
+        b2 = b1; i2 = i1;
+        b1 = d; i1 = k;
+      } else if (d < b2) {
+        b3 = b2; i3 = i2;
+        b2 = d; i2 = k;
+      } else if (d < b3) {
+        b3 = d; i3 = k;
+      }
+    }
+  }
+  if (j < n) {
+    float *o = dist2 + ((size_t)b * n + j) * 3;
+    int *oi = idx + ((size_t)b * n + j) * 3;
+    o[0] = b1; o[1] = b2; o[2] = b3;
+    oi[0] = i1; oi[1] = i2; oi[2] = i3;
+  }
+}
+
+// ---- three_interpolate (interpolate_gpu.cu:72-101): fma(p3,w3, fma(p2,w2, p1*w1)) --------------------------
+__global__ void __launch_bounds__(256) three_interpolate_kernel(int b, int c, int m, int n,
+                                                                const float *__restrict__ points,
+                                                                const int *__restrict__ idx,
+                                                                const float *__restrict__ weight,
+                                                                float *__restrict__ out) {
+  const long long total = (long long)b * c * n;
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total;
+       g += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(g % n);
+    const long long bc = g / n;
+    const int bi = (int)(bc / c);
+    const int *id = idx + ((size_t)bi * n + j) * 3;
+    const float *w = weight + ((size_t)bi * n + j) * 3;
+    const float *p = points + (size_t)bc * m;
+    out[g] = __fmaf_rn(__ldg(p + id[2]), w[2], __fmaf_rn(__ldg(p + id[1]), w[1], __fmul_rn(__ldg(p + id[0]), w[0])));
+  }
+}
+
+// ---- furthest point sampling ---------------------------------------------------------------------------------
+// POLICY_P2   : sampling_gpu.cu:69-173.  d = fma(dz,dz,fma(dy,dy,dx*dx)); points with |p|^2 <= 1e-3 are skipped;
+//               start index 0; ties resolved like the reference's shared-memory tree: smallest
+//               (bitreverse(k mod bs), k) where bs = opt_n_threads(n).
+// POLICY_TORCH: model/pointnet2_utils.py:63-84.  d = (dx*dx + dy*dy) + dz*dz (no FMA); every point is a
+//               candidate; start index given; torch.max tie rule = lowest index.
+enum { POLICY_P2 = 0, POLICY_TORCH = 1 };
+
+constexpr int kFpsThreads = 256;
+
+template <int POLICY, int PPT, typename IdxT>
+__global__ void __launch_bounds__(kFpsThreads) fps_kernel(const float *__restrict__ dataset_all, int n, int m,
+                                                          int log2bs, const long long *__restrict__ start,
+                                                          IdxT *__restrict__ idxs_all) {
+  constexpr int W = kFpsThreads / 32;
+  __shared__ unsigned long long wbest[2][W];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float *dataset = dataset_all + (size_t)b * n * 3;
+  IdxT *idxs = idxs_all + (size_t)b * m;
+  const int bs = 1 << log2bs;
+  const unsigned R = (unsigned)((n + bs - 1) >> log2bs);
+
+  float px[PPT], py[PPT], pz[PPT], td[PPT];
+  unsigned low[PPT];  // ~tie-composite; 0 marks a point that can never be selected
+#pragma unroll
+  for (int r = 0; r < PPT; ++r) {
+    const int k = tid + r * kFpsThreads;
+    px[r] = py[r] = pz[r] = 0.f;
+    td[r] = 1e10f;
+    low[r] = 0u;
+    if (k < n) {
+      px[r] = __ldg(dataset + (size_t)k * 3);
+      py[r] = __ldg(dataset + (size_t)k * 3 + 1);
+      pz[r] = __ldg(dataset + (size_t)k * 3 + 2);
+      unsigned comp;
+      bool valid = true;
+      if (POLICY == POLICY_P2) {
+        const float mag = __fmaf_rn(pz[r], pz[r], __fmaf_rn(py[r], py[r], __fmul_rn(px[r], px[r])));
+        valid = !((double)mag <= 1e-3);
+        const unsigned tb = (unsigned)k & (unsigned)(bs - 1);
+        const unsigned rev = log2bs ? (__brev(tb) >> (32 - log2bs)) : 0u;
+        comp = rev * R + ((unsigned)k >> log2bs);
+      } else {
+        comp = (unsigned)k;
+      }
+      low[r] = valid ? ~comp : 0u;
+    }
+  }
+  int old = (POLICY == POLICY_P2) ? 0 : (int)start[b];
+  if (tid == 0) idxs[0] = (IdxT)old;
+  for (int j = 1; j < m; ++j) {
+    const float x1 = __ldg(dataset + (size_t)old * 3), y1 = __ldg(dataset + (size_t)old * 3 + 1),
+                z1 = __ldg(dataset + (size_t)old * 3 + 2);
+    unsigned long long best = 0ull;
+#pragma unroll
+    for (int r = 0; r < PPT; ++r) {
+      float d;
+      if (POLICY == POLICY_P2) {
+        d = hg_dist3_fma(px[r], py[r], pz[r], x1, y1, z1);
+      } else {
+        const float dx = __fsub_rn(px[r], x1), dy = __fsub_rn(py[r], y1), dz = __fsub_rn(pz[r], z1);
+        d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+      }
+      if (low[r]) {
+        td[r] = fminf(d, td[r]);
+        // distances are >= 0, so their bit patterns order like unsigned integers; +1 keeps key 0 = "nothing"
+        const unsigned long long key = ((unsigned long long)(__float_as_uint(td[r]) + 1u) << 32) | low[r];
+        best = key > best ? key : best;
+      }
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+      const unsigned long long o = __shfl_xor_sync(0xffffffffu, best, s);
+      best = o > best ? o : best;
+    }
+    if (lane == 0) wbest[j & 1][warp] = best;
+    __syncthreads();
+    unsigned long long all = wbest[j & 1][0];
+#pragma unroll
+    for (int w = 1; w < W; ++w) {
+      const unsigned long long o = wbest[j & 1][w];
+      all = o > all ? o : all;
+    }
+    if (all == 0ull) {
+      old = 0;
+    } else {
+      const unsigned comp = ~(unsigned)(all & 0xffffffffull);
+      if (POLICY == POLICY_P2) {
+        const unsigned rev = comp / R, rr = comp % R;
+        const unsigned tb = log2bs ? (__brev(rev) >> (32 - log2bs)) : 0u;
+        old = (int)(tb + (rr << log2bs));
+      } else {
+        old = (int)comp;
+      }
+    }
+    if (tid == 0) idxs[j] = (IdxT)old;
+  }
+}
+
+template <int POLICY, typename IdxT>
+int launch_fps(const float *dataset, int b, int n, int m, const long long *start, IdxT *idxs, cudaStream_t stream) {
+  int log2bs = 0;
+  if (POLICY == POLICY_P2) {
+    const int bs = ref_opt_n_threads(n);
+    while ((1 << log2bs) < bs) ++log2bs;
+  }
+  const int ppt = (n + kFpsThreads - 1) / kFpsThreads;
+#define HG_FPS_CASE(P)                                                                                    \
+  if (ppt <= P) {                                                                                         \
+    const bool prof = hg_prof_begin(HG_PROF_FPS, stream);                                                 \
+    fps_kernel<POLICY, P, IdxT><<<b, kFpsThreads, 0, stream>>>(dataset, n, m, log2bs, start, idxs);      \
+    hg_prof_end(HG_PROF_FPS, stream, prof);                                                               \
+    HG_CHECK_LAUNCH("fps_kernel");                                                                        \
+    return HG_OK;                                                                                         \
+  }
+  HG_FPS_CASE(1)
+  HG_FPS_CASE(2)
+  HG_FPS_CASE(4)
+  HG_FPS_CASE(8)
+  HG_FPS_CASE(16)
+  HG_FPS_CASE(32)
+  HG_FPS_CASE(64)
+#undef HG_FPS_CASE
+  hg_set_error("fps: n=%d > %d points per cloud unsupported", n, 64 * kFpsThreads);
+  return HG_E_UNSUPPORTED;
+}
+
+}  // namespace
+
+// ================================================ C ABI =====================================================
+HG_API int hg_p2_gather_points(int b, int c, int n, int npoints, const float *points, const int *idx, float *out,
+                               hgStream stream_) {
+  HG_REQUIRE(points && idx && out, HG_E_BADARG, "gather_points: null pointer");
+  HG_REQUIRE(b > 0 && c > 0 && n > 0 && npoints > 0, HG_E_BADARG, "gather_points: sizes must be positive");
+  const long long total = (long long)b * c * npoints;
+  gather_channel_major_kernel<<<grid_for(total, 256), 256, 0, hg_stream(stream_)>>>(points, idx, b, c, n, npoints, out);
+  HG_CHECK_LAUNCH("gather_points");
+  return HG_OK;
+}
+
+HG_API size_t hg_p2_scatter_workspace_bytes(int b, int n, int nedges) {
+  if (b <= 0 || n <= 0 || nedges <= 0) return 0;
+  return hg_csr_workspace_bytes(b, n, nedges);
+}
+
+HG_API int hg_p2_gather_points_grad(int b, int c, int n, int npoints, const float *grad_out, const int *idx,
+                                    float *grad_points, void *workspace, size_t workspace_bytes, hgStream stream_) {
+  cudaStream_t stream = hg_stream(stream_);
+  HG_REQUIRE(grad_out && idx && grad_points, HG_E_BADARG, "gather_points_grad: null pointer");
+  HG_REQUIRE(b > 0 && c > 0 && n > 0 && npoints > 0, HG_E_BADARG, "gather_points_grad: sizes must be positive");
+  HgCsr csr;
+  int rc = hg_csr_build(idx, b, npoints, n, workspace, workspace_bytes, &csr, stream);
+  if (rc) return rc;
+  const long long total = (long long)b * c * n;
+  scatter_channel_major_kernel<1, false><<<grid_for(total, 256), 256, 0, stream>>>(grad_out, nullptr, csr.off, csr.list,
+                                                                                   b, c, n, npoints, grad_points);
+  HG_CHECK_LAUNCH("gather_points_grad");
+  return HG_OK;
+}
+
+HG_API int hg_p2_furthest_point_sampling(int b, int n, int m, const float *dataset, float *temp, int *idxs,
+                                         hgStream stream_) {
+  (void)temp;  // the reference's global scratch (sampling.cpp:74-76); distances live in registers here
+  HG_REQUIRE(dataset && idxs, HG_E_BADARG, "furthest_point_sampling: null pointer");
+  HG_REQUIRE(b > 0 && n > 0 && m >= 0, HG_E_BADARG, "furthest_point_sampling: bad sizes");
+  if (m == 0) return HG_OK;
+  return launch_fps<POLICY_P2, int>(dataset, b, n, m, nullptr, idxs, hg_stream(stream_));
+}
+
+HG_API int hg_fps_torch_f32(const float *xyz, int B, int N, int npoint, const int64_t *start, int64_t *centroids,
+                            hgStream stream_) {
+  HG_REQUIRE(xyz && start && centroids, HG_E_BADARG, "fps_torch: null pointer");
+  HG_REQUIRE(B > 0 && N > 0 && npoint >= 0, HG_E_BADARG, "fps_torch: bad sizes");
+  if (npoint == 0) return HG_OK;
+  return launch_fps<POLICY_TORCH, long long>(xyz, B, N, npoint, (const long long *)start, (long long *)centroids,
+                                             hg_stream(stream_));
+}
+
+HG_API int hg_p2_ball_query(int b, int n, int m, float radius, int nsample, const float *new_xyz, const float *xyz,
+                            int *idx, hgStream stream_) {
+  HG_REQUIRE(new_xyz && xyz && idx, HG_E_BADARG, "ball_query: null pointer");
+  HG_REQUIRE(b > 0 && n > 0 && m > 0 && nsample > 0, HG_E_BADARG, "ball_query: sizes must be positive");
+  HG_REQUIRE(b <= 65535, HG_E_UNSUPPORTED, "ball_query: b=%d > 65535", b);
+  const float radius2 = radius * radius;  // ball_query_gpu.cu:22 (FMUL)
+  ball_query_kernel<<<dim3((m + 3) / 4, b), 128, 0, hg_stream(stream_)>>>(n, m, radius2, nsample, new_xyz, xyz, idx);
+  HG_CHECK_LAUNCH("ball_query");
+  return HG_OK;
+}
+
+HG_API int hg_p2_group_points(int b, int c, int n, int npoints, int nsample, const float *points, const int *idx,
+                              float *out, hgStream stream_) {
+  HG_REQUIRE(points && idx && out, HG_E_BADARG, "group_points: null pointer");
+  HG_REQUIRE(b > 0 && c > 0 && n > 0 && npoints > 0 && nsample > 0, HG_E_BADARG, "group_points: sizes must be positive");
+  const long long total = (long long)b * c * npoints * nsample;
+  const bool prof = hg_prof_begin(HG_PROF_GROUP, hg_stream(stream_));
+  gather_channel_major_kernel<<<grid_for(total, 256), 256, 0, hg_stream(stream_)>>>(points, idx, b, c, n,
+                                                                                     npoints * nsample, out);
+  hg_prof_end(HG_PROF_GROUP, hg_stream(stream_), prof);
+  HG_CHECK_LAUNCH("group_points");
+  return HG_OK;
+}
+
+HG_API int hg_p2_group_points_grad(int b, int c, int n, int npoints, int nsample, const float *grad_out,
+                                   const int *idx, float *grad_points, void *workspace, size_t workspace_bytes,
+                                   hgStream stream_) {
+  cudaStream_t stream = hg_stream(stream_);
+  HG_REQUIRE(grad_out && idx && grad_points, HG_E_BADARG, "group_points_grad: null pointer");
+  HG_REQUIRE(b > 0 && c > 0 && n > 0 && npoints > 0 && nsample > 0, HG_E_BADARG,
+             "group_points_grad: sizes must be positive");
+  const int E = npoints * nsample;
+  HgCsr csr;
+  int rc = hg_csr_build(idx, b, E, n, workspace, workspace_bytes, &csr, stream);
+  if (rc) return rc;
+  const long long total = (long long)b * c * n;
+  scatter_channel_major_kernel<1, false><<<grid_for(total, 256), 256, 0, stream>>>(grad_out, nullptr, csr.off, csr.list,
+                                                                                   b, c, n, E, grad_points);
+  HG_CHECK_LAUNCH("group_points_grad");
+  return HG_OK;
+}
+
+HG_API int hg_p2_three_nn(int b, int n, int m, const float *unknown, const float *known, float *dist2, int *idx,
+                          hgStream stream_) {
+  HG_REQUIRE(unknown && known && dist2 && idx, HG_E_BADARG, "three_nn: null pointer");
+  HG_REQUIRE(b > 0 && n > 0 && m > 0, HG_E_BADARG, "three_nn: sizes must be positive");
+  HG_REQUIRE(b <= 65535, HG_E_UNSUPPORTED, "three_nn: b=%d > 65535", b);
+  three_nn_kernel<<<dim3((n + 127) / 128, b), 128, 0, hg_stream(stream_)>>>(n, m, unknown, known, dist2, idx);
+  HG_CHECK_LAUNCH("three_nn");
+  return HG_OK;
+}
+
+HG_API int hg_p2_three_interpolate(int b, int c, int m, int n, const float *points, const int *idx,
+                                   const float *weight, float *out, hgStream stream_) {
+  HG_REQUIRE(points && idx && weight && out, HG_E_BADARG, "three_interpolate: null pointer");
+  HG_REQUIRE(b > 0 && c > 0 && m > 0 && n > 0, HG_E_BADARG, "three_interpolate: sizes must be positive");
+  const long long total = (long long)b * c * n;
+  three_interpolate_kernel<<<grid_for(total, 256), 256, 0, hg_stream(stream_)>>>(b, c, m, n, points, idx, weight, out);
+  HG_CHECK_LAUNCH("three_interpolate");
+  return HG_OK;
+}
+
+HG_API int hg_p2_three_interpolate_grad(int b, int c, int n, int m, const float *grad_out, const int *idx,
+                                        const float *weight, float *grad_points, void *workspace,
+                                        size_t workspace_bytes, hgStream stream_) {
+  cudaStream_t stream = hg_stream(stream_);
+  HG_REQUIRE(grad_out && idx && weight && grad_points, HG_E_BADARG, "three_interpolate_grad: null pointer");
+  HG_REQUIRE(b > 0 && c > 0 && m > 0 && n > 0, HG_E_BADARG, "three_interpolate_grad: sizes must be positive");
+  HgCsr csr;
+  int rc = hg_csr_build(idx, b, n * 3, m, workspace, workspace_bytes, &csr, stream);
+  if (rc) return rc;
+  const long long total = (long long)b * c * m;
+  scatter_channel_major_kernel<3, true><<<grid_for(total, 256), 256, 0, stream>>>(grad_out, weight, csr.off, csr.list, b,
+                                                                                  c, m, n * 3, grad_points);
+  HG_CHECK_LAUNCH("three_interpolate_grad");
+  return HG_OK;
+}

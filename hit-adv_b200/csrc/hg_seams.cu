@@ -1,0 +1,190 @@
+// hg_seams.cu -- the torch-level geometry functions the PointNet++ SSG victim calls inside its forward
+// (model/pointnet2_utils.py:19-107): square_distance, query_ball_point, index_points (+ backward).
+// (farthest_point_sample lives in hg_pointnet2.cu next to the pointnet2_ops FPS it shares a kernel with.)
+//
+// Reference arithmetic, restated bit-exactly (SURVEY.md section 8 a-bis):
+//   square_distance: d[n,m] = ((-2*zz_nm) + rs_n) + rd_m, zz = FMA chain (torch.matmul), rs/rd = torch.sum(x**2,-1)
+//   query_ball_point: keep d <= float32(radius**2) ("group_idx[sqrdists > radius**2] = N"), ascending index,
+//                     first nsample, pad with the first; the reference gets there by SORTING a [B,S,N] int64
+//                     tensor (268 MB at B=64,S=512,N=1024) -- here it is one ballot-compacted scan.
+#include "hg_common.cuh"
+
+namespace {
+
+int grid_for(long long total, int threads) {
+  long long blocks = (total + threads - 1) / threads;
+  const long long cap = (long long)hg_sm_count() * 32;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+__device__ __forceinline__ float sumsq_cascade(const float *a, int C) {
+  float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
+  for (int c = 0; c < C; ++c) {
+    acc0 = __fadd_rn(acc0, __fmul_rn(a[c], a[c]));
+    if (((c + 1) & 15) == 0) {
+      acc1 = __fadd_rn(acc1, acc0);
+      acc0 = 0.f;
+      if (((c + 1) & 255) == 0) {
+        acc2 = __fadd_rn(acc2, acc1);
+        acc1 = 0.f;
+      }
+    }
+  }
+  return __fadd_rn(__fadd_rn(acc0, acc1), acc2);
+}
+
+__global__ void __launch_bounds__(256) square_distance_kernel(const float *__restrict__ src,
+                                                              const float *__restrict__ dst, int B, int N, int M,
+                                                              int C, float *__restrict__ out) {
+  const long long total = (long long)B * N * M;
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total;
+       g += (long long)gridDim.x * blockDim.x) {
+    const int m = (int)(g % M);
+    const long long bn = g / M;
+    const int b = (int)(bn / N);
+    const float *s = src + (size_t)bn * C;
+    const float *d = dst + ((size_t)b * M + m) * C;
+    float zz = __fmul_rn(s[0], d[0]);
+    for (int c = 1; c < C; ++c) zz = __fmaf_rn(s[c], d[c], zz);
+    out[g] = __fadd_rn(__fadd_rn(__fmul_rn(-2.0f, zz), sumsq_cascade(s, C)), sumsq_cascade(d, C));
+  }
+}
+
+__global__ void __launch_bounds__(128) query_ball_torch_kernel(int N, int S, float radius2, int nsample,
+                                                               const float *__restrict__ xyz,
+                                                               const float *__restrict__ new_xyz,
+                                                               long long *__restrict__ group_idx) {
+  const int b = blockIdx.y, lane = threadIdx.x & 31;
+  const int s = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (s >= S) return;
+  const float *p = xyz + (size_t)b * N * 3;
+  const float *q = new_xyz + ((size_t)b * S + s) * 3;
+  long long *o = group_idx + ((size_t)b * S + s) * nsample;
+  const float q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2);
+  const float rs = hg_sumsq3_seq(q0, q1, q2);
+  int cnt = 0, first = N;
+  for (int k0 = 0; k0 < N && cnt < nsample; k0 += 32) {
+    const int k = k0 + lane;
+    bool hit = false;
+    if (k < N) {
+      const float x = __ldg(p + (size_t)k * 3), y = __ldg(p + (size_t)k * 3 + 1), z = __ldg(p + (size_t)k * 3 + 2);
+      const float zz = hg_dot3_fma(q0, q1, q2, x, y, z);
+      const float d = __fadd_rn(__fadd_rn(__fmul_rn(-2.0f, zz), rs), hg_sumsq3_seq(x, y, z));
+      hit = !(d > radius2);
+    }
+    const unsigned mask = __ballot_sync(0xffffffffu, hit);
+    if (mask) {
+      if (cnt == 0) first = k0 + __ffs(mask) - 1;
+      const int pos = cnt + __popc(mask & ((1u << lane) - 1u));
+      if (hit && pos < nsample) o[pos] = k;
+      cnt += __popc(mask);
+    }
+  }
+  if (cnt > nsample) cnt = nsample;
+  for (int l = cnt + lane; l < nsample; l += 32) o[l] = first;  // empty ball -> N, as the reference's sort leaves it
+}
+
+// index_points: out[b,e,:] = points[b, idx[b,e], :]
+__global__ void __launch_bounds__(256) index_points_kernel(const float *__restrict__ points,
+                                                           const long long *__restrict__ idx, int B, int N, int C,
+                                                           int M, float *__restrict__ out) {
+  const long long total = (long long)B * M * C;
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total;
+       g += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(g % C);
+    const long long be = g / C;
+    const int b = (int)(be / M);
+    const long long a = idx[be];
+    out[g] = __ldg(points + ((size_t)b * N + (size_t)a) * C + c);
+  }
+}
+
+__global__ void idx64_to_keys_kernel(const long long *__restrict__ idx, long long total, int N, int *__restrict__ keys) {
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total;
+       g += (long long)gridDim.x * blockDim.x) {
+    const long long a = idx[g];
+    keys[g] = (a >= 0 && a < N) ? (int)a : -1;
+  }
+}
+
+// grad_points[b,n,:] = sum over edges e with idx[b,e]==n, ascending e, of grad_out[b,e,:]
+__global__ void __launch_bounds__(256) index_points_grad_kernel(const float *__restrict__ grad_out,
+                                                                const int *__restrict__ off,
+                                                                const int *__restrict__ list, int B, int N, int C,
+                                                                int M, float *__restrict__ grad_points) {
+  const long long total = (long long)B * N * C;
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total;
+       g += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(g % C);
+    const long long bn = g / C;
+    const int b = (int)(bn / N), n = (int)(bn % N);
+    const int *o = off + (size_t)b * (N + 1);
+    const int *l = list + (size_t)b * M;
+    float acc = 0.f;
+    for (int q = o[n]; q < o[n + 1]; ++q) acc = __fadd_rn(acc, grad_out[((size_t)b * M + l[q]) * C + c]);
+    grad_points[g] = acc;
+  }
+}
+
+}  // namespace
+
+HG_API int hg_square_distance_f32(const float *src, const float *dst, int B, int N, int M, int C, float *out,
+                                  hgStream stream_) {
+  HG_REQUIRE(src && dst && out, HG_E_BADARG, "square_distance: null pointer");
+  HG_REQUIRE(B > 0 && N > 0 && M > 0 && C > 0, HG_E_BADARG, "square_distance: sizes must be positive");
+  const long long total = (long long)B * N * M;
+  square_distance_kernel<<<grid_for(total, 256), 256, 0, hg_stream(stream_)>>>(src, dst, B, N, M, C, out);
+  HG_CHECK_LAUNCH("square_distance");
+  return HG_OK;
+}
+
+HG_API int hg_query_ball_torch_f32(float radius2, int nsample, const float *xyz, const float *new_xyz, int B, int N,
+                                   int S, int64_t *group_idx, hgStream stream_) {
+  HG_REQUIRE(xyz && new_xyz && group_idx, HG_E_BADARG, "query_ball_torch: null pointer");
+  HG_REQUIRE(B > 0 && N > 0 && S > 0 && nsample > 0, HG_E_BADARG, "query_ball_torch: sizes must be positive");
+  HG_REQUIRE(B <= 65535, HG_E_UNSUPPORTED, "query_ball_torch: B=%d > 65535", B);
+  query_ball_torch_kernel<<<dim3((S + 3) / 4, B), 128, 0, hg_stream(stream_)>>>(N, S, radius2, nsample, xyz, new_xyz,
+                                                                                (long long *)group_idx);
+  HG_CHECK_LAUNCH("query_ball_torch");
+  return HG_OK;
+}
+
+HG_API int hg_index_points_f32(const float *points, const int64_t *idx, int B, int N, int C, int M, float *out,
+                               hgStream stream_) {
+  HG_REQUIRE(points && idx && out, HG_E_BADARG, "index_points: null pointer");
+  HG_REQUIRE(B > 0 && N > 0 && C > 0 && M > 0, HG_E_BADARG, "index_points: sizes must be positive");
+  const long long total = (long long)B * M * C;
+  index_points_kernel<<<grid_for(total, 256), 256, 0, hg_stream(stream_)>>>(points, (const long long *)idx, B, N, C, M,
+                                                                            out);
+  HG_CHECK_LAUNCH("index_points");
+  return HG_OK;
+}
+
+HG_API size_t hg_index_points_grad_workspace_bytes(int B, int N, int M) {
+  if (B <= 0 || N <= 0 || M <= 0) return 0;
+  return hg_align((size_t)B * M * sizeof(int)) + hg_csr_workspace_bytes(B, N, M);
+}
+
+HG_API int hg_index_points_grad_f32(const float *grad_out, const int64_t *idx, int B, int N, int C, int M,
+                                    float *grad_points, void *workspace, size_t workspace_bytes, hgStream stream_) {
+  cudaStream_t stream = hg_stream(stream_);
+  HG_REQUIRE(grad_out && idx && grad_points, HG_E_BADARG, "index_points_grad: null pointer");
+  HG_REQUIRE(B > 0 && N > 0 && C > 0 && M > 0, HG_E_BADARG, "index_points_grad: sizes must be positive");
+  HG_REQUIRE(workspace && workspace_bytes >= hg_index_points_grad_workspace_bytes(B, N, M), HG_E_WORKSPACE,
+             "index_points_grad: workspace too small");
+  int *keys = (int *)workspace;
+  void *csr_ws = (char *)workspace + hg_align((size_t)B * M * sizeof(int));
+  const long long te = (long long)B * M;
+  idx64_to_keys_kernel<<<grid_for(te, 256), 256, 0, stream>>>((const long long *)idx, te, N, keys);
+  HG_CHECK_LAUNCH("idx64_to_keys");
+  HgCsr csr;
+  int rc = hg_csr_build(keys, B, M, N, csr_ws, hg_csr_workspace_bytes(B, N, M), &csr, stream);
+  if (rc) return rc;
+  const long long total = (long long)B * N * C;
+  index_points_grad_kernel<<<grid_for(total, 256), 256, 0, stream>>>(grad_out, csr.off, csr.list, B, N, C, M,
+                                                                     grad_points);
+  HG_CHECK_LAUNCH("index_points_grad");
+  return HG_OK;
+}

@@ -1,0 +1,249 @@
+"""Tensor-level entry points: thin wrappers that hand raw device pointers to the C ABI (include/hitgeom.h)
+and the `torch.autograd.Function`s whose backward reuses the saved nearest-neighbour indices.
+
+No arithmetic on point data happens in Python/PyTorch here; torch only allocates outputs and workspaces."""
+import torch
+
+from . import _lib
+from ._lib import check, lib, ptr, require, stream_ptr, workspace
+
+MODE_CHAMFER, MODE_HAUSDORFF = 0, 1
+
+
+# ------------------------------------------------------------------------------------------------------------
+# set distance (util/set_distance.py)
+# ------------------------------------------------------------------------------------------------------------
+def nn_bidir(gts, preds):
+    """Fused `batch_pairwise_dist(gts, preds)` + `torch.min(P,1)` + `torch.min(P,2)` (set_distance.py:15-48).
+
+    gts [B,N2,D], preds [B,N1,D] -> (min1 [B,N1], arg1 [B,N1] int32, min2 [B,N2], arg2 [B,N2] int32)."""
+    require(gts, "gts", ndim=3)
+    require(preds, "preds", ndim=3)
+    B, N2, D = gts.shape
+    if preds.shape[0] != B or preds.shape[2] != D:
+        raise RuntimeError(f"shape mismatch: gts {tuple(gts.shape)} vs preds {tuple(preds.shape)}")
+    N1 = preds.shape[1]
+    dev = gts.device
+    min1 = torch.empty((B, N1), dtype=torch.float32, device=dev)
+    min2 = torch.empty((B, N2), dtype=torch.float32, device=dev)
+    arg1 = torch.empty((B, N1), dtype=torch.int32, device=dev)
+    arg2 = torch.empty((B, N2), dtype=torch.int32, device=dev)
+    nbytes = lib().hg_nn_bidir_workspace_bytes(B, N2, N1, D)
+    ws = workspace(nbytes, dev)
+    check(lib().hg_nn_bidir_f32(ptr(gts), ptr(preds), B, N2, N1, D, ptr(min1), ptr(arg1), ptr(min2), ptr(arg2),
+                                ptr(ws), ws.numel(), stream_ptr()), "hg_nn_bidir_f32")
+    return min1, arg1, min2, arg2
+
+
+def pairwise_dist(x, y):
+    require(x, "x", ndim=3)
+    require(y, "y", ndim=3)
+    B, Nx, D = x.shape
+    Ny = y.shape[1]
+    P = torch.empty((B, Nx, Ny), dtype=torch.float32, device=x.device)
+    check(lib().hg_pairwise_dist_f32(ptr(x), ptr(y), B, Nx, Ny, D, ptr(P), stream_ptr()), "hg_pairwise_dist_f32")
+    return P
+
+
+def set_loss(min1, min2, mode):
+    B, N1 = min1.shape
+    N2 = min2.shape[1]
+    dev = min1.device
+    loss1 = torch.empty(B, dtype=torch.float32, device=dev)
+    loss2 = torch.empty(B, dtype=torch.float32, device=dev)
+    hd1 = torch.empty(B, dtype=torch.int32, device=dev) if mode == MODE_HAUSDORFF else None
+    hd2 = torch.empty(B, dtype=torch.int32, device=dev) if mode == MODE_HAUSDORFF else None
+    check(lib().hg_set_loss_f32(ptr(min1), ptr(min2), B, N1, N2, mode, ptr(loss1), ptr(loss2), ptr(hd1), ptr(hd2),
+                                stream_ptr()), "hg_set_loss_f32")
+    return loss1, loss2, hd1, hd2
+
+
+def set_loss_bwd(gts, preds, arg1, arg2, hd1, hd2, g1, g2, mode, want_gts):
+    B, N2, D = gts.shape
+    N1 = preds.shape[1]
+    dev = gts.device
+    grad_preds = torch.empty_like(preds)
+    grad_gts = torch.empty_like(gts) if want_gts else None
+    ws = workspace(lib().hg_set_loss_bwd_workspace_bytes(B, N2, N1), dev)
+    check(lib().hg_set_loss_bwd_f32(ptr(gts), ptr(preds), ptr(arg1), ptr(arg2), ptr(hd1), ptr(hd2), ptr(g1), ptr(g2), B,
+                                    N2, N1, D, mode, ptr(grad_preds), ptr(grad_gts), ptr(ws), ws.numel(),
+                                    stream_ptr()), "hg_set_loss_bwd_f32")
+    return grad_preds, grad_gts
+
+
+class SetDistanceFn(torch.autograd.Function):
+    """(preds, gts) -> (loss1 [B], loss2 [B]) for Chamfer (mode 0) / Hausdorff (mode 1)."""
+
+    @staticmethod
+    def forward(ctx, preds, gts, mode):
+        preds_c = preds.detach().contiguous()
+        gts_c = gts.detach().contiguous()
+        min1, arg1, min2, arg2 = nn_bidir(gts_c, preds_c)
+        loss1, loss2, hd1, hd2 = set_loss(min1, min2, mode)
+        ctx.mode = mode
+        ctx.saved = (preds_c, gts_c, arg1, arg2, hd1, hd2)
+        return loss1, loss2
+
+    @staticmethod
+    def backward(ctx, g1, g2):
+        preds_c, gts_c, arg1, arg2, hd1, hd2 = ctx.saved
+        B = preds_c.shape[0]
+        dev = preds_c.device
+        g1 = torch.zeros(B, device=dev) if g1 is None else g1.to(torch.float32).contiguous()
+        g2 = torch.zeros(B, device=dev) if g2 is None else g2.to(torch.float32).contiguous()
+        need_p, need_g = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        grad_preds, grad_gts = set_loss_bwd(gts_c, preds_c, arg1, arg2, hd1, hd2, g1, g2, ctx.mode, need_g)
+        return (grad_preds if need_p else None), (grad_gts if need_g else None), None
+
+
+def _as_points(t, name):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor (hitgeom has no CPU path)")
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"{name} must be float32, got {t.dtype}")
+    if t.dim() != 3:
+        raise RuntimeError(f"{name} must be [B,N,D], got shape {tuple(t.shape)}")
+    return t
+
+
+def chamfer_losses(preds, gts):
+    """`ChamferDistance.forward(preds, gts)` (set_distance.py:40-50) -> (loss1 [B], loss2 [B])."""
+    return SetDistanceFn.apply(_as_points(preds, "preds"), _as_points(gts, "gts"), MODE_CHAMFER)
+
+
+def hausdorff_losses(preds, gts):
+    """`HausdorffDistance.forward(preds, gts)` (set_distance.py:58-70)."""
+    return SetDistanceFn.apply(_as_points(preds, "preds"), _as_points(gts, "gts"), MODE_HAUSDORFF)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# kNN (util/dist_utils.py KNNDist, model/dgcnn_cls.py knn, pytorch3d.ops.knn_points)
+# ------------------------------------------------------------------------------------------------------------
+def knn_self(pc, k1, want_vals=True):
+    """k1 smallest per row of dist[i,j] = (xx_j + (-2 zz_ij)) + xx_i.  pc [B,K,C] point-major.
+
+    Returns (vals [B,K,k1] ascending or None, idx [B,K,k1] int32)."""
+    require(pc, "pc", ndim=3)
+    B, K, C = pc.shape
+    dev = pc.device
+    vals = torch.empty((B, K, k1), dtype=torch.float32, device=dev) if want_vals else None
+    idx = torch.empty((B, K, k1), dtype=torch.int32, device=dev)
+    ws = workspace(lib().hg_knn_self_workspace_bytes(B, K, C, k1), dev)
+    check(lib().hg_knn_self_f32(ptr(pc), B, K, C, k1, ptr(vals), ptr(idx), ptr(ws), ws.numel(), stream_ptr()),
+          "hg_knn_self_f32")
+    return vals, idx
+
+
+class KnnOutlierFn(torch.autograd.Function):
+    """pc [B,K,3] point-major -> per-sample kNN-outlier loss [B] (dist_utils.py:148-167, unit weights)."""
+
+    @staticmethod
+    def forward(ctx, pc, k, alpha):
+        pc_c = pc.detach().contiguous()
+        B, K, C = pc_c.shape
+        dev = pc_c.device
+        vals, idx = knn_self(pc_c, k + 1)
+        value = torch.empty((B, K), dtype=torch.float32, device=dev)
+        mask = torch.empty((B, K), dtype=torch.float32, device=dev)
+        loss = torch.empty(B, dtype=torch.float32, device=dev)
+        check(lib().hg_knn_outlier_fwd_f32(ptr(vals), B, K, k + 1, float(alpha), None, ptr(value), ptr(mask), ptr(loss),
+                                           stream_ptr()), "hg_knn_outlier_fwd_f32")
+        ctx.saved = (pc_c, idx, mask)
+        ctx.k1 = k + 1
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        pc_c, idx, mask = ctx.saved
+        B, K, C = pc_c.shape
+        g = g.to(torch.float32).contiguous()
+        grad = torch.empty_like(pc_c)
+        ws = workspace(lib().hg_knn_outlier_bwd_workspace_bytes(B, K, ctx.k1), pc_c.device)
+        check(lib().hg_knn_outlier_bwd_f32(ptr(pc_c), ptr(idx), ptr(mask), ptr(g), B, K, C, ctx.k1, ptr(grad), ptr(ws),
+                                           ws.numel(), stream_ptr()), "hg_knn_outlier_bwd_f32")
+        return grad, None, None
+
+
+def knn_outlier_loss(pc, k, alpha):
+    return KnnOutlierFn.apply(_as_points(pc, "pc"), int(k), float(alpha))
+
+
+def knn_points_raw(p1, p2, K):
+    require(p1, "p1", ndim=3)
+    require(p2, "p2", ndim=3)
+    B, N, _ = p1.shape
+    M = p2.shape[1]
+    dists = torch.empty((B, N, K), dtype=torch.float32, device=p1.device)
+    idx = torch.empty((B, N, K), dtype=torch.int64, device=p1.device)
+    check(lib().hg_knn_points_f32(ptr(p1), ptr(p2), B, N, M, K, ptr(dists), ptr(idx), stream_ptr()), "hg_knn_points_f32")
+    return dists, idx
+
+
+# ------------------------------------------------------------------------------------------------------------
+# torch-level seams of model/pointnet2_utils.py
+# ------------------------------------------------------------------------------------------------------------
+def square_distance(src, dst):
+    require(src, "src", ndim=3)
+    require(dst, "dst", ndim=3)
+    B, N, C = src.shape
+    M = dst.shape[1]
+    out = torch.empty((B, N, M), dtype=torch.float32, device=src.device)
+    check(lib().hg_square_distance_f32(ptr(src), ptr(dst), B, N, M, C, ptr(out), stream_ptr()), "hg_square_distance_f32")
+    return out
+
+
+def fps_torch(xyz, npoint, start):
+    require(xyz, "xyz", ndim=3)
+    require(start, "start", dtype=torch.int64, ndim=1)
+    B, N, _ = xyz.shape
+    out = torch.empty((B, npoint), dtype=torch.int64, device=xyz.device)
+    check(lib().hg_fps_torch_f32(ptr(xyz), B, N, npoint, ptr(start), ptr(out), stream_ptr()), "hg_fps_torch_f32")
+    return out
+
+
+def query_ball_torch(radius, nsample, xyz, new_xyz):
+    require(xyz, "xyz", ndim=3)
+    require(new_xyz, "new_xyz", ndim=3)
+    B, N, _ = xyz.shape
+    S = new_xyz.shape[1]
+    out = torch.empty((B, S, nsample), dtype=torch.int64, device=xyz.device)
+    r2 = float(torch.tensor(radius ** 2, dtype=torch.float32))  # the float32 rounding torch applies to the scalar
+    check(lib().hg_query_ball_torch_f32(r2, nsample, ptr(xyz), ptr(new_xyz), B, N, S, ptr(out), stream_ptr()),
+          "hg_query_ball_torch_f32")
+    return out
+
+
+class IndexPointsFn(torch.autograd.Function):
+    """points [B,N,C], idx [B,M] int64 -> [B,M,C]; backward is a deterministic segmented sum."""
+
+    @staticmethod
+    def forward(ctx, points, idx):
+        pts = points.detach().contiguous()
+        B, N, C = pts.shape
+        M = idx.shape[1]
+        out = torch.empty((B, M, C), dtype=torch.float32, device=pts.device)
+        check(lib().hg_index_points_f32(ptr(pts), ptr(idx), B, N, C, M, ptr(out), stream_ptr()), "hg_index_points_f32")
+        ctx.saved = (idx, N)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        idx, N = ctx.saved
+        g = grad_out.to(torch.float32).contiguous()
+        B, M, C = g.shape
+        grad = torch.empty((B, N, C), dtype=torch.float32, device=g.device)
+        ws = workspace(lib().hg_index_points_grad_workspace_bytes(B, N, M), g.device)
+        check(lib().hg_index_points_grad_f32(ptr(g), ptr(idx), B, N, C, M, ptr(grad), ptr(ws), ws.numel(), stream_ptr()),
+              "hg_index_points_grad_f32")
+        return grad, None
+
+
+def tune_nn_bidir(T=0, RB=0):
+    """Benchmark-only override of the nn_bidir tile shape (0 = automatic)."""
+    lib().hg_nn_bidir_tune(int(T), int(RB))
+
+
+__all__ = [n for n in dir() if not n.startswith("_")]
+_ = _lib

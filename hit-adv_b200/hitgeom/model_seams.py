@@ -1,0 +1,51 @@
+"""Kernel-backed versions of the torch-level geometry functions the victims call inside forward:
+
+  model/pointnet2_utils.py:19-40   square_distance(src, dst)
+  model/pointnet2_utils.py:43-60   index_points(points, idx)                 (differentiable in points)
+  model/pointnet2_utils.py:63-84   farthest_point_sample(xyz, npoint)        (random start: torch.randint)
+  model/pointnet2_utils.py:87-107  query_ball_point(radius, nsample, xyz, new_xyz)
+  model/dgcnn_cls.py:7-13          knn(x, k)                                 (x is channel-major [B,C,N])
+
+Same signatures, dtypes (int64 indices) and semantics, so `hitgeom.install()` can rebind them into the
+reference's module globals and PointNet++ SSG / DGCNN run unchanged (`sample_and_group` and
+`get_graph_feature` look the names up at call time).
+"""
+import torch
+
+from . import functional as F
+
+
+def square_distance(src, dst):
+    """[B,N,C] x [B,M,C] -> [B,N,M] = ((-2 src.dst) + |src|^2) + |dst|^2, the reference's rounding order."""
+    return F.square_distance(src.contiguous(), dst.contiguous())
+
+
+def index_points(points, idx):
+    """points [B,N,C], idx [B,S] or [B,S,ns] (int64) -> [B,S,C] / [B,S,ns,C]."""
+    B = points.shape[0]
+    flat = idx.reshape(B, -1).contiguous()
+    if flat.dtype != torch.int64:
+        flat = flat.long()
+    out = F.IndexPointsFn.apply(points, flat)
+    return out.view(*idx.shape, points.shape[-1])
+
+
+def farthest_point_sample(xyz, npoint):
+    """xyz [B,N,3] -> centroids [B,npoint] int64.  The start index is drawn exactly as the reference does
+    (`torch.randint(0, N, (B,))` on the CPU generator, pointnet2_utils.py:75), so a seeded run reproduces it."""
+    device = xyz.device
+    B, N, C = xyz.shape
+    farthest = torch.randint(0, N, (B,), dtype=torch.long).to(device)
+    return F.fps_torch(xyz.detach().contiguous(), int(npoint), farthest)
+
+
+def query_ball_point(radius, nsample, xyz, new_xyz):
+    """xyz [B,N,3], new_xyz [B,S,3] -> group_idx [B,S,nsample] int64 (ascending, padded with the first hit)."""
+    return F.query_ball_torch(radius, int(nsample), xyz.detach().contiguous(), new_xyz.detach().contiguous())
+
+
+def knn(x, k):
+    """DGCNN kNN: x [B,C,N] -> idx [B,N,k] int64, the k largest of -||x_i - x_j||^2 (self included)."""
+    pc = x.detach().transpose(2, 1).contiguous()  # kernels are point-major
+    _, idx = F.knn_self(pc, int(k), want_vals=False)
+    return idx.long()

@@ -1,0 +1,5 @@
+"""hitgeom.pointnet2_ops -- drop-in for the reference's `pointnet2_ops` package
+(pointnet2_ops_lib/pointnet2_ops): `_ext` (the native module) and `pointnet2_utils` (autograd wrappers)."""
+from . import _ext  # noqa: F401
+from . import ops  # noqa: F401
+from . import ops as pointnet2_utils  # noqa: F401  (reference module name)

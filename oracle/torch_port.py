@@ -1,0 +1,90 @@
+"""CPU restatement of the reference's *torch* path for the loss classes -- the same tensor program the reference
+executes (three `bmm`, diagonal gather, two `min`; `matmul` + `topk`; autograd for the backward), written from
+the formulas in util/set_distance.py:15-70 and util/dist_utils.py:56-80,136-175,279-294.
+
+TEST INFRASTRUCTURE ONLY (see oracle/hitgeom_oracle.c).  Two uses:
+  * bench.py's `cpu_baseline` and `--impl reference` legs time THIS on the GPU box's host cores: it is what
+    the reference's CPU path costs (materialised [B,N,N] matrices, autograd-saved copies and all), which the
+    matrix-free C oracle would understate;
+  * tests/test_oracle_golden.py checks it against the golden vectors, so the timed program is the pinned one.
+Pinned against tests/golden/loss_classes.npz and setdist_*.npz (bit-exact on this container's torch 2.11/MKL).
+"""
+import torch
+
+
+def pairwise(x, y):
+    """P[b,i,j] = |x_i|^2 + |y_j|^2 - 2 x_i.y_j with the squared norms read off the Gram diagonals."""
+    xx = torch.bmm(x, x.transpose(2, 1))
+    yy = torch.bmm(y, y.transpose(2, 1))
+    zz = torch.bmm(x, y.transpose(2, 1))
+    ix = torch.arange(x.shape[1])
+    iy = torch.arange(y.shape[1])
+    rx = xx[:, ix, ix].unsqueeze(1).expand_as(zz.transpose(2, 1))
+    ry = yy[:, iy, iy].unsqueeze(1).expand_as(zz)
+    return rx.transpose(2, 1) + ry - 2 * zz
+
+
+def chamfer(preds, gts):
+    P = pairwise(gts, preds)
+    return torch.min(P, 1)[0].mean(dim=1), torch.min(P, 2)[0].mean(dim=1)
+
+
+def hausdorff(preds, gts):
+    P = pairwise(gts, preds)
+    return torch.min(P, 1)[0].max(dim=1)[0], torch.min(P, 2)[0].max(dim=1)[0]
+
+
+def _pick(l1, l2, method):
+    return l1 if method == "adv2ori" else l2 if method == "ori2adv" else (l1 + l2) / 2.0
+
+
+def _weighted(loss, weights, batch_avg):
+    if weights is None:
+        weights = torch.ones(loss.shape[0])
+    loss = loss * weights.float()
+    return loss.mean() if batch_avg else loss
+
+
+def chamfer_dist(adv, ori, method="adv2ori", weights=None, batch_avg=True):
+    return _weighted(_pick(*chamfer(adv, ori), method), weights, batch_avg)
+
+
+def hausdorff_dist(adv, ori, method="adv2ori", weights=None, batch_avg=True):
+    return _weighted(_pick(*hausdorff(adv, ori), method), weights, batch_avg)
+
+
+def knn_dist(pc, k=5, alpha=1.05, weights=None, batch_avg=True):
+    if pc.shape[1] != 3:
+        pc = pc.transpose(2, 1)
+    inner = -2.0 * torch.matmul(pc.transpose(2, 1), pc)
+    xx = torch.sum(pc ** 2, dim=1, keepdim=True)
+    dist = xx + inner + xx.transpose(2, 1)
+    neg_value, _ = (-dist).topk(k=k + 1, dim=-1)
+    value = torch.mean(-(neg_value[..., 1:]), dim=-1)
+    with torch.no_grad():
+        threshold = torch.mean(value, dim=-1) + alpha * torch.std(value, dim=-1)
+        mask = (value > threshold[:, None]).float()
+    return _weighted(torch.mean(value * mask, dim=1), weights, batch_avg)
+
+
+def chamfer_knn_dist(adv, ori, weights=None, batch_avg=True, chamfer_method="adv2ori", knn_k=5, knn_alpha=1.05,
+                     chamfer_weight=5.0, knn_weight=3.0):
+    return (chamfer_dist(adv, ori, chamfer_method, weights, batch_avg) * chamfer_weight
+            + knn_dist(adv, knn_k, knn_alpha, weights, batch_avg) * knn_weight)
+
+
+def step_chamfer_knn(adv, ori):
+    """One fwd+bwd of the CW-kNN distance term (CW/kNN.py:104-108): returns (loss, d loss / d adv)."""
+    a = adv.detach().clone().requires_grad_()
+    loss = chamfer_knn_dist(a, ori, batch_avg=False).sum()
+    loss.backward()
+    return loss.detach(), a.grad
+
+
+def step_cd_hd_knn(adv, ori):
+    """Config 1: ChamferDist + HausdorffDist + KNNDist(k=5) fwd+bwd."""
+    a = adv.detach().clone().requires_grad_()
+    loss = (chamfer_dist(a, ori, batch_avg=False) + hausdorff_dist(a, ori, batch_avg=False)
+            + knn_dist(a, batch_avg=False)).sum()
+    loss.backward()
+    return loss.detach(), a.grad

@@ -1,0 +1,172 @@
+"""Parity of the CUDA Chamfer / Hausdorff path (through the Python mirror -> C ABI) against the golden
+vectors of the reference and against the CPU oracle.  Bar: min values and argmin indices BIT-EXACT;
+losses within 1e-6 relative; gradients within 1e-5 norm-wise per sample."""
+import numpy as np
+import pytest
+import torch
+
+from util_inputs import clouds, jitter, normwise
+
+pytestmark = pytest.mark.gpu
+
+
+def gpu(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+@pytest.fixture(scope="module")
+def F():
+    from hitgeom import functional
+
+    return functional
+
+
+@pytest.mark.parametrize("name", ["setdist_eq", "setdist_ragged", "setdist_dups"])
+@pytest.mark.parametrize("T", [0, 8, 16])
+def test_nn_bidir_golden(golden, F, name, T):
+    g = golden(name)
+    F.tune_nn_bidir(T, 0)
+    try:
+        m1, a1, m2, a2 = F.nn_bidir(gpu(g["gts"]), gpu(g["preds"]))
+    finally:
+        F.tune_nn_bidir(0, 0)
+    assert np.array_equal(m1.cpu().numpy(), g["min1"])
+    assert np.array_equal(m2.cpu().numpy(), g["min2"])
+    assert np.array_equal(a1.cpu().numpy(), g["arg1"])
+    assert np.array_equal(a2.cpu().numpy(), g["arg2"])
+
+
+@pytest.mark.parametrize("B,N2,N1,kind", [(1, 1, 1, "gauss"), (2, 7, 5, "gauss"), (3, 33, 129, "gauss"),
+                                          (2, 513, 511, "surface"), (2, 1024, 1024, "surface"),
+                                          (1, 3000, 2049, "gauss"), (5, 64, 640, "surface")])
+@pytest.mark.parametrize("T,RB", [(0, 0), (8, 8), (16, 24), (16, 256)])
+def test_nn_bidir_vs_oracle(oracle, F, B, N2, N1, kind, T, RB):
+    gts = clouds(B, N2, 100 + N2, kind)
+    preds = jitter(clouds(B, N1, 100 + N2, kind), 7) if N1 != N2 else jitter(gts, 7)
+    F.tune_nn_bidir(T, RB)
+    try:
+        m1, a1, m2, a2 = F.nn_bidir(gpu(gts), gpu(preds))
+    finally:
+        F.tune_nn_bidir(0, 0)
+    o1, oa1, o2, oa2 = oracle.nn_bidir(gts, preds, threads=4)
+    assert np.array_equal(m1.cpu().numpy(), o1) and np.array_equal(m2.cpu().numpy(), o2)
+    assert np.array_equal(a1.cpu().numpy(), oa1) and np.array_equal(a2.cpu().numpy(), oa2)
+
+
+def test_nn_bidir_identical_clouds_ties(oracle, F):
+    """adv == ori and many exact duplicates: every tie must resolve to the first index like torch.min."""
+    gts = clouds(2, 300, 5, "surface")
+    gts[:, 100:200] = gts[:, 0:100]
+    m1, a1, m2, a2 = F.nn_bidir(gpu(gts), gpu(gts.copy()))
+    o1, oa1, o2, oa2 = oracle.nn_bidir(gts, gts)
+    assert np.array_equal(a1.cpu().numpy(), oa1) and np.array_equal(a2.cpu().numpy(), oa2)
+    assert np.array_equal(m1.cpu().numpy(), o1) and np.array_equal(m2.cpu().numpy(), o2)
+
+
+@pytest.mark.parametrize("name", ["setdist_eq", "setdist_ragged", "setdist_dups"])
+@pytest.mark.parametrize("tag", ["ch", "hd"])
+def test_losses_and_grads_golden(golden, name, tag):
+    from hitgeom.set_distance import chamfer, hausdorff
+
+    g = golden(name)
+    fn = chamfer if tag == "ch" else hausdorff
+    w = gpu(g["w"])
+    for which in (0, 1):
+        p = gpu(g["preds"]).requires_grad_()
+        x = gpu(g["gts"]).requires_grad_()
+        losses = fn(p, x)
+        (losses[which] * w).sum().backward()
+        ref = g[f"{tag}_loss{which + 1}"]
+        np.testing.assert_allclose(losses[which].detach().cpu().numpy(), ref, rtol=1e-6 if tag == "ch" else 0, atol=0)
+        assert normwise(p.grad.cpu().numpy(), g[f"{tag}_grad_preds{which + 1}"]) < 1e-5
+        assert normwise(x.grad.cpu().numpy(), g[f"{tag}_grad_gts{which + 1}"]) < 1e-5
+
+
+def test_channel_first_degenerate(golden, oracle):
+    """[B,3,K] inputs -> 3x3 matrix with inner dim K.  The CUDA generic-D kernel uses the same
+    sequential FMA chain as the oracle (bit-exact vs oracle); vs the reference's MKL GEMM the difference is
+    summation-order noise, bounded in ulps of the cancelling operands."""
+    from hitgeom.set_distance import chamfer
+
+    g = golden("setdist_channel_first")
+    P = chamfer.batch_pairwise_dist(gpu(g["gts"]), gpu(g["preds"])).cpu().numpy()
+    assert np.array_equal(P, oracle.pairwise_dist(g["gts"], g["preds"]))
+    ulp = np.spacing(np.float32(np.abs(g["P"]).max()))
+    assert np.abs(P - g["P"]).max() <= 32 * ulp
+    p = gpu(g["preds"]).requires_grad_()
+    l1, l2 = chamfer(p, gpu(g["gts"]))
+    assert np.abs(l1.detach().cpu().numpy() - g["ch_loss1"]).max() <= 32 * ulp
+    assert np.abs(l2.detach().cpu().numpy() - g["ch_loss2"]).max() <= 32 * ulp
+    ((l1 + 2 * l2) * gpu(g["w"])).sum().backward()
+    # gradient: same argmins as the reference here (3x3 with a clear diagonal) -> 1e-4 of the norm
+    assert normwise(p.grad.cpu().numpy(), g["grad_preds"]) < 1e-4
+
+
+def test_loss_classes_golden(golden):
+    from hitgeom.dist_utils import ChamferDist, ChamferkNNDist, HausdorffDist
+
+    g = golden("loss_classes")
+    ori = gpu(g["ori"])
+    w = torch.from_numpy(g["w"])  # float64 CPU tensor, as CW/Perturb.py:148-150 passes it
+    for cls, tag in [(ChamferDist, "chamfer"), (HausdorffDist, "hausdorff")]:
+        for method in ("adv2ori", "ori2adv", "both"):
+            for wt, wtag in [(None, "now"), (w, "w")]:
+                for avg in (True, False):
+                    a = gpu(g["adv"]).requires_grad_()
+                    loss = cls(method=method)(a, ori, weights=wt, batch_avg=avg)
+                    loss.sum().backward()
+                    key = f"{tag}_{method}_{wtag}_{'avg' if avg else 'vec'}"
+                    np.testing.assert_allclose(loss.detach().cpu().numpy(), g[key], rtol=2e-6, atol=0, err_msg=key)
+                    gr, ref = a.grad.cpu().numpy(), g[key + "_grad"]
+                    assert np.abs(gr - ref).max() <= 1e-5 * np.abs(ref).max(), key
+    a = gpu(g["adv"]).requires_grad_()
+    loss = ChamferkNNDist()(a, ori, weights=w, batch_avg=True)
+    loss.backward()
+    np.testing.assert_allclose(loss.item(), g["chamferknn"], rtol=2e-6)
+    assert np.abs(a.grad.cpu().numpy() - g["chamferknn_grad"]).max() <= 1e-5 * np.abs(g["chamferknn_grad"]).max()
+    a = gpu(g["adv"]).requires_grad_()
+    loss = ChamferkNNDist(chamfer_method="both", knn_k=4, knn_alpha=1.1, chamfer_weight=2.0, knn_weight=0.5)(
+        a, ori, batch_avg=False)
+    loss.sum().backward()
+    np.testing.assert_allclose(loss.detach().cpu().numpy(), g["chamferknn2"], rtol=2e-6)
+    assert normwise(a.grad.cpu().numpy(), g["chamferknn2_grad"]) < 1e-5
+
+
+def test_config1_full_size_vs_oracle(oracle, F):
+    """BASELINE config 1 shape: 388 x 1024 clouds vs jittered copies -- bit-exact against the oracle."""
+    ori = clouds(388, 1024, 1234)
+    adv = jitter(ori, 99)
+    m1, a1, m2, a2 = F.nn_bidir(gpu(ori), gpu(adv))
+    o1, oa1, o2, oa2 = oracle.nn_bidir(ori, adv, threads=oracle.host_threads())
+    assert np.array_equal(m1.cpu().numpy(), o1) and np.array_equal(m2.cpu().numpy(), o2)
+    assert np.array_equal(a1.cpu().numpy(), oa1) and np.array_equal(a2.cpu().numpy(), oa2)
+
+
+def test_large_cloud_properties(F):
+    """Config 5 shape (16384 points per cloud): size-independent properties, no oracle pass needed.
+    (i) a cloud against itself: every min is attained at the point itself or an exact duplicate, and the
+    value equals the reference formula evaluated at (i,i); (ii) permuting preds permutes arg2 consistently."""
+    x = clouds(3, 16384, 77)
+    xg = gpu(x)
+    m1, a1, m2, a2 = F.nn_bidir(xg, xg.clone())
+    a1c, a2c = a1.cpu().numpy(), a2.cpu().numpy()
+    assert np.array_equal(x[np.arange(3)[:, None], a1c], x) and np.array_equal(x[np.arange(3)[:, None], a2c], x)
+    perm = np.random.default_rng(0).permutation(16384)
+    y = jitter(x, 3)
+    _, _, m2a, a2a = F.nn_bidir(xg, gpu(y))
+    _, _, m2b, a2b = F.nn_bidir(xg, gpu(y[:, perm]))
+    assert np.array_equal(m2a.cpu().numpy(), m2b.cpu().numpy())
+    assert np.array_equal(y[np.arange(3)[:, None], a2a.cpu().numpy()], y[:, perm][np.arange(3)[:, None], a2b.cpu().numpy()])
+
+
+def test_errors_are_exceptions(F):
+    from hitgeom import HitgeomError
+
+    with pytest.raises(RuntimeError):
+        F.nn_bidir(torch.zeros(1, 4, 3), torch.zeros(1, 4, 3))  # CPU tensors
+    with pytest.raises(RuntimeError):
+        F.nn_bidir(torch.zeros(1, 4, 3, device="cuda").transpose(1, 2), torch.zeros(1, 4, 3, device="cuda"))
+    with pytest.raises(RuntimeError):
+        F.nn_bidir(torch.zeros(1, 4, 3, device="cuda", dtype=torch.float64), torch.zeros(1, 4, 3, device="cuda"))
+    with pytest.raises((HitgeomError, RuntimeError)):
+        F.knn_self(torch.zeros(1, 4, 3, device="cuda"), 9)  # k > K

@@ -94,3 +94,29 @@ def test_dgcnn_knn_bit_exact(golden, oracle, C, k):
     if C != 3:
         ref_vals = -np.take_along_axis(g[f"pw{C}"], g[f"idx{C}_k{k}"], axis=2)
         assert np.array_equal(vals, ref_vals)
+
+
+def test_torch_port_matches_golden(golden):
+    """The torch-op restatement that bench.py times as the CPU baseline is the pinned program."""
+    import torch
+
+    from oracle import torch_port as tp
+
+    g = golden("loss_classes")
+    adv, ori, w = torch.from_numpy(g["adv"]), torch.from_numpy(g["ori"]), torch.from_numpy(g["w"])
+    for method in ("adv2ori", "ori2adv", "both"):
+        a = adv.clone().requires_grad_()
+        loss = tp.chamfer_dist(a, ori, method, w, batch_avg=False)
+        loss.sum().backward()
+        assert np.array_equal(loss.detach().numpy(), g[f"chamfer_{method}_w_vec"])
+        assert np.array_equal(a.grad.numpy(), g[f"chamfer_{method}_w_vec_grad"])
+        assert np.array_equal(tp.hausdorff_dist(adv, ori, method, None, True).numpy(), g[f"hausdorff_{method}_now_avg"])
+    a = adv.clone().requires_grad_()
+    loss = tp.knn_dist(a, 5, 1.05, None, batch_avg=False)
+    loss.sum().backward()
+    assert np.array_equal(loss.detach().numpy(), g["knn_k5_BK3_now"])
+    assert np.array_equal(a.grad.numpy(), g["knn_k5_BK3_now_grad"])
+    a = adv.clone().requires_grad_()
+    loss = tp.chamfer_knn_dist(a, ori, weights=w, batch_avg=True)
+    loss.backward()
+    assert np.array_equal(loss.detach().numpy(), g["chamferknn"])
