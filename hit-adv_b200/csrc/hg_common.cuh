@@ -66,8 +66,15 @@ __device__ __forceinline__ float hg_dot3_fma(float a0, float a1, float a2, float
 __device__ __forceinline__ float hg_sumsq3_seq(float a0, float a1, float a2) {
   return __fadd_rn(__fadd_rn(__fmul_rn(a0, a0), __fmul_rn(a1, a1)), __fmul_rn(a2, a2));
 }
-// nvcc -O3 contraction of (ax-bx)*(ax-bx) + (ay-by)*(ay-by) + (az-bz)*(az-bz) in the pointnet2_ops kernels
+// nvcc -O3 contraction of (ax-bx)*(ax-bx) + (ay-by)*(ay-by) + (az-bz)*(az-bz) in the pointnet2_ops kernels:
+// fma(dz,dz, fma(dx,dx, round(dy*dy))) -- in `a*a + b*b` the LEFT product is fused, the right one rounded (read
+// off the SASS of query_ball_point_kernel / three_nn_kernel / furthest_point_sampling_kernel built for sm_100).
 __device__ __forceinline__ float hg_dist3_fma(float ax, float ay, float az, float bx, float by, float bz) {
+  const float dx = __fsub_rn(ax, bx), dy = __fsub_rn(ay, by), dz = __fsub_rn(az, bz);
+  return __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+}
+// pytorch3d knn_points: `dist += diff*diff` per coordinate -> fma(dz,dz, fma(dy,dy, dx*dx))
+__device__ __forceinline__ float hg_dist3_seq(float ax, float ay, float az, float bx, float by, float bz) {
   const float dx = __fsub_rn(ax, bx), dy = __fsub_rn(ay, by), dz = __fsub_rn(az, bz);
   return __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
 }

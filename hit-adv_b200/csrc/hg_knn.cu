@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(kKnnThreads) knn3_kernel(const float *__restri
         const float nzz = __fmaf_rn(n2, c.z, __fmaf_rn(n1, c.y, __fmul_rn(n0, c.x)));  // == -2*zz exactly
         d = __fadd_rn(__fadd_rn(c.w, nzz), qq);
       } else {
-        d = hg_dist3_fma(q0, q1, q2, c.x, c.y, c.z);
+        d = hg_dist3_seq(q0, q1, q2, c.x, c.y, c.z);
       }
       top.push(d, base + t);
     }

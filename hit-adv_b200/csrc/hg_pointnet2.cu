@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(128) three_nn_kernel(int n, int m, const float
   }
 }
 
-// ---- three_interpolate (interpolate_gpu.cu:72-101): fma(p3,w3, fma(p2,w2, p1*w1)) --------------------------
+// ---- three_interpolate (interpolate_gpu.cu:72-101): fma(p3,w3, fma(p1,w1, round(p2*w2))) -------------------
 __global__ void __launch_bounds__(256) three_interpolate_kernel(int b, int c, int m, int n,
                                                                 const float *__restrict__ points,
                                                                 const int *__restrict__ idx,
@@ -175,12 +175,12 @@ __global__ void __launch_bounds__(256) three_interpolate_kernel(int b, int c, in
     const int *id = idx + ((size_t)bi * n + j) * 3;
     const float *w = weight + ((size_t)bi * n + j) * 3;
     const float *p = points + (size_t)bc * m;
-    out[g] = __fmaf_rn(__ldg(p + id[2]), w[2], __fmaf_rn(__ldg(p + id[1]), w[1], __fmul_rn(__ldg(p + id[0]), w[0])));
+    out[g] = __fmaf_rn(__ldg(p + id[2]), w[2], __fmaf_rn(__ldg(p + id[0]), w[0], __fmul_rn(__ldg(p + id[1]), w[1])));
   }
 }
 
 // ---- furthest point sampling ---------------------------------------------------------------------------------
-// POLICY_P2   : sampling_gpu.cu:69-173.  d = fma(dz,dz,fma(dy,dy,dx*dx)); points with |p|^2 <= 1e-3 are skipped;
+// POLICY_P2   : sampling_gpu.cu:69-173.  d = fma(dz,dz,fma(dx,dx,dy*dy)); points with |p|^2 <= 1e-3 are skipped;
 //               start index 0; ties resolved like the reference's shared-memory tree: smallest
 //               (bitreverse(k mod bs), k) where bs = opt_n_threads(n).
 // POLICY_TORCH: model/pointnet2_utils.py:63-84.  d = (dx*dx + dy*dy) + dz*dz (no FMA); every point is a
@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(kFpsThreads) fps_kernel(const float *__restric
       unsigned comp;
       bool valid = true;
       if (POLICY == POLICY_P2) {
-        const float mag = __fmaf_rn(pz[r], pz[r], __fmaf_rn(py[r], py[r], __fmul_rn(px[r], px[r])));
+        const float mag = __fmaf_rn(pz[r], pz[r], __fmaf_rn(px[r], px[r], __fmul_rn(py[r], py[r])));
         valid = !((double)mag <= 1e-3);
         const unsigned tb = (unsigned)k & (unsigned)(bs - 1);
         const unsigned rev = log2bs ? (__brev(tb) >> (32 - log2bs)) : 0u;

@@ -20,7 +20,7 @@
  * is an individually rounded FP32 operation and every fmaf() is a single-rounded fused multiply-add.
  *   dot_fma(a,b)  = fma(a[D-1],b[D-1], ... fma(a[1],b[1], a[0]*b[0]))   <- torch.bmm/matmul, small inner dim
  *   sumsq_seq(a)  = ((a0*a0 + a1*a1) + a2*a2) [cascade of 16s for C>=16] <- torch.sum(x**2, dim)
- *   dist_fma(a,b) = fma(dz,dz, fma(dy,dy, dx*dx)), dx=a0-b0 ...          <- nvcc -O3 contraction of the
+ *   dist_fma(a,b) = fma(dz,dz, fma(dx,dx, dy*dy)), dx=a0-b0 ...          <- nvcc -O3 contraction of the
  *                                                                          pointnet2_ops .cu expressions
  */
 #include <math.h>
@@ -59,7 +59,17 @@ static inline float sumsq_seq(const float *a, int D) {
   return (acc0 + acc1) + acc2;
 }
 
+/* nvcc -O3 contracts  dx*dx + dy*dy + dz*dz  as fma(dz,dz, fma(dx,dx, round(dy*dy))): in `a*a + b*b` the LEFT
+ * product is fused and the right one rounded.  Read off the SASS of the reference built for sm_100
+ * (query_ball_point_kernel, three_nn_kernel, furthest_point_sampling_kernel) and pinned by
+ * tests/golden/pointnet2_ref.npz, which those kernels produced on a B200. */
 static inline float dist_fma3(float ax, float ay, float az, float bx, float by, float bz) {
+  float dx = ax - bx, dy = ay - by, dz = az - bz;
+  return fmaf(dz, dz, fmaf(dx, dx, dy * dy));
+}
+
+/* pytorch3d's kernel accumulates `dist += diff*diff` coordinate by coordinate: fma(dz,dz, fma(dy,dy, dx*dx)) */
+static inline float dist_seq3(float ax, float ay, float az, float bx, float by, float bz) {
   float dx = ax - bx, dy = ay - by, dz = az - bz;
   return fmaf(dz, dz, fmaf(dy, dy, dx * dx));
 }
@@ -335,7 +345,7 @@ ORC_API int orc_knn_points(const float *p1, const float *p2, int B, int N, int M
       int64_t *id = idx + ((size_t)b * N + i) * K;
       int cnt = 0;
       for (int j = 0; j < M; ++j) {
-        float d = dist_fma3(q[i * 3], q[i * 3 + 1], q[i * 3 + 2], r[j * 3], r[j * 3 + 1], r[j * 3 + 2]);
+        float d = dist_seq3(q[i * 3], q[i * 3 + 1], q[i * 3 + 2], r[j * 3], r[j * 3 + 1], r[j * 3 + 2]);
         if (cnt < K || d < v[cnt - 1]) {
           int t = cnt < K ? cnt : K - 1;
           while (t > 0 && d < v[t - 1]) {
@@ -449,7 +459,7 @@ ORC_API int orc_p2_fps(const float *dataset_all, int B, int n, int m, int *idxs_
         float best = -1;
         for (int k = tid; k < n; k += bs) {
           float x2 = dataset[k * 3], y2 = dataset[k * 3 + 1], z2 = dataset[k * 3 + 2];
-          float mag = fmaf(z2, z2, fmaf(y2, y2, x2 * x2));
+          float mag = fmaf(z2, z2, fmaf(x2, x2, y2 * y2));
           if ((double)mag <= 1e-3) continue;
           float d = dist_fma3(x2, y2, z2, x1, y1, z1);
           float d2 = d < temp[k] ? d : temp[k];
@@ -581,7 +591,7 @@ ORC_API int orc_p2_three_nn(const float *unknown, const float *known, int b, int
   return 0;
 }
 
-/* interpolate_gpu.cu:72-101: out = p1*w1 + p2*w2 + p3*w3, nvcc contraction fma(p3,w3, fma(p2,w2, p1*w1)) */
+/* interpolate_gpu.cu:72-101: out = p1*w1 + p2*w2 + p3*w3, nvcc contraction fma(p3,w3, fma(p1,w1, round(p2*w2))) */
 ORC_API int orc_p2_three_interpolate(const float *points, const int *idx, const float *weight, int b, int c,
                                      int m, int n, float *out) {
   for (int bi = 0; bi < b; ++bi)
@@ -590,7 +600,7 @@ ORC_API int orc_p2_three_interpolate(const float *points, const int *idx, const 
         const int *id = idx + ((size_t)bi * n + j) * 3;
         const float *w = weight + ((size_t)bi * n + j) * 3;
         const float *p = points + ((size_t)bi * c + l) * m;
-        out[((size_t)bi * c + l) * n + j] = fmaf(p[id[2]], w[2], fmaf(p[id[1]], w[1], p[id[0]] * w[0]));
+        out[((size_t)bi * c + l) * n + j] = fmaf(p[id[2]], w[2], fmaf(p[id[0]], w[0], p[id[1]] * w[1]));
       }
   return 0;
 }

@@ -120,3 +120,30 @@ def test_torch_port_matches_golden(golden):
     loss = tp.chamfer_knn_dist(a, ori, weights=w, batch_avg=True)
     loss.backward()
     assert np.array_equal(loss.detach().numpy(), g["chamferknn"])
+
+
+# ---- pointnet2_ops: fixtures produced ON A B200 by the reference's own kernels (tests/golden/make_golden_gpu.py) ----
+def test_p2_fps_matches_reference_kernel(golden, oracle):
+    g = golden("pointnet2_ref")
+    for tag in "abc":
+        ref = g[f"fps_{tag}_idx"]
+        assert np.array_equal(oracle.p2_fps(g[f"fps_{tag}_xyz"], ref.shape[1]), ref), tag
+
+
+def test_p2_ball_query_group_match_reference_kernel(golden, oracle):
+    g = golden("pointnet2_ref")
+    xyz, new_xyz = g["bq_xyz"], g["bq_new_xyz"]
+    assert np.array_equal(oracle.p2_fps(xyz, 51), g["bq_fps"])
+    assert np.array_equal(oracle.p2_gather(xyz.transpose(0, 2, 1), g["bq_fps"]).transpose(0, 2, 1), new_xyz)
+    for key in g.files:
+        if key.startswith("bq_r"):
+            r, ns = float(key.split("_")[1][1:]), int(key.split("_")[2][2:])
+            assert np.array_equal(oracle.p2_ball_query(new_xyz, xyz, r, ns), g[key]), key
+    assert np.array_equal(oracle.p2_group(g["grp_points"], g["bq_r0.2_ns32"]), g["grp_out"])
+
+
+def test_p2_three_nn_interpolate_match_reference_kernel(golden, oracle):
+    g = golden("pointnet2_ref")
+    d2, idx = oracle.p2_three_nn(g["nn_unknown"], g["nn_known"])
+    assert np.array_equal(d2, g["nn_dist2"]) and np.array_equal(idx, g["nn_idx"])
+    assert np.array_equal(oracle.p2_three_interpolate(g["ti_feats"], g["nn_idx"], g["ti_w"]), g["ti_out"])
