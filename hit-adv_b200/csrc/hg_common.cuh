@@ -109,3 +109,11 @@ struct HgCsr {
 };
 int hg_csr_build(const int *keys, int B, int E, int N, void *workspace, size_t workspace_bytes, HgCsr *out,
                  cudaStream_t stream);
+
+// ---- 3-D streaming kNN (hg_knn3.cu) ---------------------------------------------------------------------------
+#define HG_KNN_FORM_EXPANDED 0  // dist = (xx_j + (-2 zz)) + xx_i   (KNNDist / DGCNN)
+#define HG_KNN_FORM_DIRECT 1    // dist = fma(dz,dz, fma(dy,dy, dx*dx))   (pytorch3d knn_points)
+int hg_knn3_launch_i32(int form, const float *q, const float *r, int B, int Nq, int Nr, int k1, float *vals, int *idx,
+                       cudaStream_t stream);
+int hg_knn3_launch_i64(int form, const float *q, const float *r, int B, int Nq, int Nr, int k1, float *vals,
+                       long long *idx, cudaStream_t stream);

@@ -9,133 +9,10 @@
 //   zz   = fma(p_i[C-1],p_j[C-1], ... p_i[0]*p_j[0])                 torch.matmul, sequential FMA chain
 //   dist[i,j] = (xx_j + (-2*zz)) + xx_i      (DGCNN's pairwise_distance is exactly -dist)
 // Selection: the k1 smallest per row, ascending, lowest index first among equal values (canonical order;
-// torch.topk leaves tie order unspecified).  The matrix [B,K,K] is never stored for C == 3.
+// torch.topk leaves tie order unspecified).  The matrix [B,K,K] is never stored for C == 3 (hg_knn3.cu).
 #include "hg_common.cuh"
 
 namespace {
-
-// ---- register-resident sorted list ---------------------------------------------------------------------------
-// Candidates arrive in ascending index order; a candidate enters only if strictly smaller than the current
-// last element and bubbles up while strictly smaller than its predecessor => lowest index first on ties.
-template <int KM>
-struct TopK {
-  float v[KM];
-  int id[KM];
-  __device__ __forceinline__ void init() {
-#pragma unroll
-    for (int t = 0; t < KM; ++t) {
-      v[t] = CUDART_INF_F;
-      id[t] = 0;
-    }
-  }
-  __device__ __forceinline__ void push(float d, int j) {
-    if (d < v[KM - 1]) {
-      v[KM - 1] = d;
-      id[KM - 1] = j;
-#pragma unroll
-      for (int t = KM - 1; t > 0; --t) {
-        if (v[t] < v[t - 1]) {
-          const float tv = v[t];
-          v[t] = v[t - 1];
-          v[t - 1] = tv;
-          const int ti = id[t];
-          id[t] = id[t - 1];
-          id[t - 1] = ti;
-        }
-      }
-    }
-  }
-};
-
-constexpr int kKnnThreads = 128;
-constexpr int kKnnTile = 512;
-
-enum { FORM_EXPANDED = 0, FORM_DIRECT = 1 };
-
-// One thread per query, reference points streamed through shared memory (broadcast LDS.128).
-// FORM_EXPANDED: q = refs = pc (self kNN), dist as above.  FORM_DIRECT: squared L2 of differences.
-template <int KM, int FORM, typename IdxT>
-__global__ void __launch_bounds__(kKnnThreads) knn3_kernel(const float *__restrict__ queries,
-                                                           const float *__restrict__ refs, int Nq, int Nr, int k1,
-                                                           float *__restrict__ vals, IdxT *__restrict__ idx) {
-  __shared__ float4 tile[kKnnTile];
-  const int b = blockIdx.y;
-  const int i = blockIdx.x * kKnnThreads + threadIdx.x;
-  const float *q = queries + (size_t)b * Nq * 3;
-  const float *r = refs + (size_t)b * Nr * 3;
-  float q0 = 0.f, q1 = 0.f, q2 = 0.f, qq = 0.f;
-  if (i < Nq) {
-    q0 = __ldg(q + (size_t)i * 3);
-    q1 = __ldg(q + (size_t)i * 3 + 1);
-    q2 = __ldg(q + (size_t)i * 3 + 2);
-    qq = hg_sumsq3_seq(q0, q1, q2);
-  }
-  const float n0 = -2.0f * q0, n1 = -2.0f * q1, n2 = -2.0f * q2;
-  TopK<KM> top;
-  top.init();
-  for (int base = 0; base < Nr; base += kKnnTile) {
-    __syncthreads();
-    for (int t = threadIdx.x; t < kKnnTile; t += kKnnThreads) {
-      const int j = base + t;
-      float4 v = make_float4(0.f, 0.f, 0.f, CUDART_INF_F);
-      if (j < Nr) {
-        v.x = __ldg(r + (size_t)j * 3);
-        v.y = __ldg(r + (size_t)j * 3 + 1);
-        v.z = __ldg(r + (size_t)j * 3 + 2);
-        v.w = (FORM == FORM_EXPANDED) ? hg_sumsq3_seq(v.x, v.y, v.z) : 0.f;
-      }
-      tile[t] = v;
-    }
-    __syncthreads();
-    const int lim = min(kKnnTile, Nr - base);
-#pragma unroll 4
-    for (int t = 0; t < lim; ++t) {
-      const float4 c = tile[t];
-      float d;
-      if (FORM == FORM_EXPANDED) {
-        const float nzz = __fmaf_rn(n2, c.z, __fmaf_rn(n1, c.y, __fmul_rn(n0, c.x)));  // == -2*zz exactly
-        d = __fadd_rn(__fadd_rn(c.w, nzz), qq);
-      } else {
-        d = hg_dist3_seq(q0, q1, q2, c.x, c.y, c.z);
-      }
-      top.push(d, base + t);
-    }
-  }
-  if (i < Nq) {
-#pragma unroll
-    for (int t = 0; t < KM; ++t) {
-      if (t < k1) {
-        if (vals) vals[((size_t)b * Nq + i) * k1 + t] = top.v[t];
-        idx[((size_t)b * Nq + i) * k1 + t] = (IdxT)top.id[t];
-      }
-    }
-  }
-}
-
-template <int FORM, typename IdxT>
-int launch_knn3(const float *q, const float *r, int B, int Nq, int Nr, int k1, float *vals, IdxT *idx,
-                cudaStream_t stream) {
-  dim3 grid((Nq + kKnnThreads - 1) / kKnnThreads, B);
-#define HG_KNN_CASE(KM)                                                                              \
-  if (k1 <= KM) {                                                                                    \
-    const bool prof = hg_prof_begin(HG_PROF_KNN, stream);                                            \
-    knn3_kernel<KM, FORM, IdxT><<<grid, kKnnThreads, 0, stream>>>(q, r, Nq, Nr, k1, vals, idx);      \
-    hg_prof_end(HG_PROF_KNN, stream, prof);                                                          \
-    HG_CHECK_LAUNCH("knn3_kernel");                                                                  \
-    return HG_OK;                                                                                    \
-  }
-  HG_KNN_CASE(4)
-  HG_KNN_CASE(6)
-  HG_KNN_CASE(8)
-  HG_KNN_CASE(12)
-  HG_KNN_CASE(17)
-  HG_KNN_CASE(20)
-  HG_KNN_CASE(24)
-  HG_KNN_CASE(32)
-#undef HG_KNN_CASE
-  hg_set_error("knn: k=%d > 32 unsupported", k1);
-  return HG_E_UNSUPPORTED;
-}
 
 // ---- generic channel count (DGCNN edge-conv layers 2-4: C = 64, 64, 128) ------------------------------------
 // xx with ATen's cascade-sum order (levels of 16): probed bit-exact for C = 64, 128.
@@ -379,7 +256,7 @@ HG_API int hg_knn_self_f32(const float *pc, int B, int K, int C, int k1, float *
   HG_REQUIRE(B > 0 && K > 0 && C > 0, HG_E_BADARG, "knn_self: sizes must be positive");
   HG_REQUIRE(k1 >= 1 && k1 <= 32 && k1 <= K, HG_E_BADARG, "knn_self: need 1 <= k <= min(32, K); got k=%d K=%d", k1, K);
   HG_REQUIRE(B <= 65535, HG_E_UNSUPPORTED, "knn_self: B=%d > 65535 clouds per call", B);
-  if (C == 3) return launch_knn3<FORM_EXPANDED, int>(pc, pc, B, K, K, k1, vals, idx, stream);
+  if (C == 3) return hg_knn3_launch_i32(HG_KNN_FORM_EXPANDED, pc, pc, B, K, K, k1, vals, idx, stream);
   const size_t need = hg_knn_self_workspace_bytes(B, K, C, k1);
   HG_REQUIRE(workspace && workspace_bytes >= need, HG_E_WORKSPACE, "knn_self: workspace too small (%zu < %zu)",
              workspace_bytes, need);
@@ -413,7 +290,7 @@ HG_API int hg_knn_points_f32(const float *p1, const float *p2, int B, int N, int
   HG_REQUIRE(B > 0 && N > 0 && M > 0, HG_E_BADARG, "knn_points: sizes must be positive");
   HG_REQUIRE(K >= 1 && K <= 32 && K <= M, HG_E_BADARG, "knn_points: need 1 <= K <= min(32, M); got K=%d M=%d", K, M);
   HG_REQUIRE(B <= 65535, HG_E_UNSUPPORTED, "knn_points: B=%d > 65535 clouds per call", B);
-  return launch_knn3<FORM_DIRECT, long long>(p1, p2, B, N, M, K, dists, (long long *)idx, hg_stream(stream_));
+  return hg_knn3_launch_i64(HG_KNN_FORM_DIRECT, p1, p2, B, N, M, K, dists, (long long *)idx, hg_stream(stream_));
 }
 
 HG_API int hg_knn_outlier_fwd_f32(const float *vals, int B, int K, int k1, float alpha, const float *weights,

@@ -49,13 +49,14 @@ __device__ __forceinline__ float nn_p_exact(float x0, float x1, float x2, float 
   return __fadd_rn(__fadd_rn(rx, ry), t);
 }
 
+// launch bounds: T=16 -> 12 warps per SM (3 per scheduler, <= 170 registers); T=8 -> 20 warps per SM (<= 102)
 template <int T, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) nn_bidir_d3_kernel(NnParams p) {
+__global__ void __launch_bounds__(WARPS * 32, (T == 8 ? 20 : 12) / WARPS) nn_bidir_d3_kernel(NnParams p) {
   static_assert(T % 2 == 0, "columns are processed as packed pairs");
   constexpr int TP = T / 2;
   extern __shared__ float4 smem[];
   float4 *xs = smem;                                            // [RB] (-2x0,-2x1,-2x2,rx)
-  uint4 *rowpart = reinterpret_cast<uint4 *>(smem + p.RB);      // [WARPS][RB/2] (m_a,mask_a,m_b,mask_b)
+  uint4 *rowpart = reinterpret_cast<uint4 *>(smem + p.RB + 2);  // [WARPS][RB/2] (m_a,mask_a,m_b,mask_b)
 
   const int b = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -66,10 +67,10 @@ __global__ void __launch_bounds__(WARPS * 32) nn_bidir_d3_kernel(NnParams p) {
 
   // ---- stage the row block: (-2x, rx); rows past N2 get rx=+inf so they never win a minimum -----------------
   const float *gx = p.gts + (size_t)b * p.N2 * 3;
-  for (int r = threadIdx.x; r < p.RB; r += WARPS * 32) {
+  for (int r = threadIdx.x; r < p.RB + 2; r += WARPS * 32) {  // +2: the prefetch of the last iteration
     const int i = r0 + r;
     float4 v = make_float4(0.f, 0.f, 0.f, CUDART_INF_F);
-    if (i < p.N2) {
+    if (i < p.N2 && r < p.RB) {
       const float x0 = __ldg(gx + (size_t)i * 3), x1 = __ldg(gx + (size_t)i * 3 + 1), x2 = __ldg(gx + (size_t)i * 3 + 2);
       v = make_float4(-2.0f * x0, -2.0f * x1, -2.0f * x2, hg_dot3_fma(x0, x1, x2, x0, x1, x2));
     }
@@ -112,10 +113,11 @@ __global__ void __launch_bounds__(WARPS * 32) nn_bidir_d3_kernel(NnParams p) {
     }
     uint4 *myrow = rowpart + (size_t)warp * (p.RB / 2);
 
+    float4 xa = xs[0], xb = xs[1];
     for (int rb = 0; rb < p.RB; rb += kColBatch) {
 #pragma unroll
       for (int rr = 0; rr < kColBatch; rr += 2) {
-        const float4 xa = xs[rb + rr], xb = xs[rb + rr + 1];
+        const float4 xa_next = xs[rb + rr + 2], xb_next = xs[rb + rr + 3];  // software prefetch (LDS latency)
         float2 pa[TP], pb[TP];
 #pragma unroll
         for (int q = 0; q < TP; ++q) {
@@ -142,6 +144,8 @@ __global__ void __launch_bounds__(WARPS * 32) nn_bidir_d3_kernel(NnParams p) {
         const unsigned ka = __ballot_sync(0xffffffffu, ma == wa);
         const unsigned kb = __ballot_sync(0xffffffffu, mb == wb);
         if (lane == 0) myrow[(rb + rr) >> 1] = make_uint4(__float_as_uint(wa), ka, __float_as_uint(wb), kb);
+        xa = xa_next;
+        xb = xb_next;
       }
       const int batch = (r0 + rb) / kColBatch;
 #pragma unroll
@@ -407,7 +411,7 @@ template <int T, int WARPS>
 int launch_main(const NnParams &p, int B, cudaStream_t stream) {
   const int ncg = (p.N1 + 32 * T - 1) / (32 * T);
   dim3 grid((p.N2 + p.RB - 1) / p.RB, (ncg + WARPS - 1) / WARPS, B);
-  const size_t smem = (size_t)p.RB * sizeof(float4) + (size_t)WARPS * (p.RB / 2) * sizeof(uint4);
+  const size_t smem = (size_t)(p.RB + 2) * sizeof(float4) + (size_t)WARPS * (p.RB / 2) * sizeof(uint4);
   const bool prof = hg_prof_begin(HG_PROF_NN_BIDIR, stream);
   nn_bidir_d3_kernel<T, WARPS><<<grid, WARPS * 32, smem, stream>>>(p);
   hg_prof_end(HG_PROF_NN_BIDIR, stream, prof);
@@ -470,13 +474,20 @@ HG_API int hg_nn_bidir_f32(const float *gts, const float *preds, int B, int N2, 
   p.rowres = (unsigned long long *)((char *)workspace + hg_align((size_t)B * N1 * 8));
   HG_CUDA(cudaMemsetAsync(workspace, 0xff, need, stream));
 
-  int T = g_force_T ? g_force_T : (N1 > 256 ? 16 : 8);
-  // rows per CTA: enough CTAs to fill the machine several times over, but amortise the column load
+  int T = g_force_T ? g_force_T : (N1 >= 2048 ? 16 : 8);
+  // rows per CTA: amortise the per-CTA column load and result merge (measured: >= 128 rows is flat, 64 costs
+  // ~10%), but keep several waves of CTAs on the machine
   int RB = g_force_RB;
   if (!RB) {
-    RB = 64;
-    const long long ctas_at_64 = (long long)B * ((N2 + 63) / 64) * ((N1 + 32 * T * 2 - 1) / (32 * T * 2));
-    if (ctas_at_64 > (long long)hg_sm_count() * 64 && N2 >= 1024) RB = 128;
+    const int ncg_ = (N1 + 32 * T - 1) / (32 * T);
+    const int wpc = (ncg_ >= 4 && ncg_ % 4 == 0) ? 4 : (ncg_ >= 2 ? 2 : 1);
+    RB = 256;
+    while (RB > 32) {
+      const long long ctas = (long long)B * ((N2 + RB - 1) / RB) * ((ncg_ + wpc - 1) / wpc);
+      if (ctas * wpc >= (long long)hg_sm_count() * 12 * 4) break;  // >= 4 waves of 12 warps per SM
+      RB >>= 1;
+    }
+    if (RB > N2) RB = (N2 + kColBatch - 1) / kColBatch * kColBatch;
   }
   RB = (RB + kColBatch - 1) / kColBatch * kColBatch;
   if (RB > 1024) RB = 1024;
