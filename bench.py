@@ -316,6 +316,9 @@ def main_hitgeom(args):
     sharding.barrier()
     e2e_ms = sharding.max_over_ranks(e0.elapsed_time(e1) / args.steps)
 
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
     if rank != 0:
         return
     pk, pk_src = peaks()

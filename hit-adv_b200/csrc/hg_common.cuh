@@ -109,6 +109,19 @@ struct HgCsr {
 };
 int hg_csr_build(const int *keys, int B, int E, int N, void *workspace, size_t workspace_bytes, HgCsr *out,
                  cudaStream_t stream);
+// Same layout, built with parallel integer atomics: entries of a segment are in arbitrary order, walk them with
+// hg_csr_next() to get ascending edge order (deterministic sums without a stable sort).
+int hg_csr_build_unordered(const int *keys, int B, int E, int N, void *workspace, size_t workspace_bytes, HgCsr *out,
+                           cudaStream_t stream);
+// smallest entry of list[p0..p1) that is greater than `last` (INT_MAX if none)
+__device__ __forceinline__ int hg_csr_next(const int *__restrict__ list, int p0, int p1, int last) {
+  int best = 0x7fffffff;
+  for (int q = p0; q < p1; ++q) {
+    const int e = list[q];
+    if (e > last && e < best) best = e;
+  }
+  return best;
+}
 
 // ---- 3-D streaming kNN (hg_knn3.cu) ---------------------------------------------------------------------------
 #define HG_KNN_FORM_EXPANDED 0  // dist = (xx_j + (-2 zz)) + xx_i   (KNNDist / DGCNN)

@@ -94,3 +94,92 @@ int hg_csr_build(const int *keys, int B, int E, int N, void *workspace, size_t w
   out->list = list;
   return HG_OK;
 }
+
+// ---- unordered variant for the hot-loop backward passes ---------------------------------------------------------
+// Same off/list layout, but the position of an edge inside its destination's segment is taken from an integer
+// atomic (fully parallel over the edges, no serial placement).  Consumers then walk a segment in ascending edge
+// order with hg_csr_next() (selection over the few entries), so the summation order -- and the result -- is still
+// independent of how the atomics resolved.  Segments are tiny on this path (Chamfer: multiplicity <= ~3; kNN:
+// only edges leaving outlier points), which is what makes the O(c^2) walk cheaper than a stable sort.
+namespace {
+
+__global__ void __launch_bounds__(256) csr_count_kernel(const int *__restrict__ keys, long long total, int E, int N,
+                                                        int *__restrict__ off_all) {
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total;
+       g += (long long)gridDim.x * blockDim.x) {
+    const int key = keys[g];
+    if (key >= 0 && key < N) atomicAdd(off_all + (g / E) * (N + 1) + key + 1, 1);
+  }
+}
+
+__global__ void __launch_bounds__(256) csr_scan_kernel(int N, int *__restrict__ off_all, int *__restrict__ cursor_all) {
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int *off = off_all + (size_t)b * (N + 1);
+  int *cursor = cursor_all + (size_t)b * N;
+  __shared__ int warp_tot[8];
+  __shared__ int carry_s;
+  if (tid == 0) carry_s = 0;
+  __syncthreads();
+  for (int base = 1; base <= N; base += 256) {
+    const int i = base + tid;
+    int v = (i <= N) ? off[i] : 0;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, v, d);
+      if (lane >= d) v += t;
+    }
+    if (lane == 31) warp_tot[warp] = v;
+    __syncthreads();
+    int add = carry_s;
+    for (int w = 0; w < warp; ++w) add += warp_tot[w];
+    if (i <= N) {
+      off[i] = v + add;
+      if (i < N) cursor[i] = v + add;  // start of segment i
+    }
+    __syncthreads();
+    if (tid == 255) carry_s = v + add;
+    __syncthreads();
+  }
+  if (tid == 0) cursor[0] = 0;
+}
+
+__global__ void __launch_bounds__(256) csr_fill_kernel(const int *__restrict__ keys, long long total, int E, int N,
+                                                       int *__restrict__ cursor_all, int *__restrict__ list_all) {
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total;
+       g += (long long)gridDim.x * blockDim.x) {
+    const int key = keys[g];
+    if (key >= 0 && key < N) {
+      const long long b = g / E;
+      const int pos = atomicAdd(cursor_all + b * N + key, 1);
+      list_all[b * E + pos] = (int)(g - b * E);
+    }
+  }
+}
+
+}  // namespace
+
+int hg_csr_build_unordered(const int *keys, int B, int E, int N, void *workspace, size_t workspace_bytes, HgCsr *out,
+                           cudaStream_t stream) {
+  HG_REQUIRE(workspace && workspace_bytes >= hg_csr_workspace_bytes(B, N, E), HG_E_WORKSPACE,
+             "csr: workspace too small (%zu < %zu)", workspace_bytes, hg_csr_workspace_bytes(B, N, E));
+  char *p = (char *)workspace;
+  int *off = (int *)p;
+  p += hg_align((size_t)B * (N + 1) * sizeof(int));
+  int *cursor = (int *)p;
+  p += hg_align((size_t)B * N * sizeof(int));
+  int *list = (int *)p;
+  HG_CUDA(cudaMemsetAsync(off, 0, (size_t)B * (N + 1) * sizeof(int), stream));
+  const long long total = (long long)B * E;
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)hg_sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  csr_count_kernel<<<(int)blocks, 256, 0, stream>>>(keys, total, E, N, off);
+  HG_CHECK_LAUNCH("csr_count_kernel");
+  csr_scan_kernel<<<B, 256, 0, stream>>>(N, off, cursor);
+  HG_CHECK_LAUNCH("csr_scan_kernel");
+  csr_fill_kernel<<<(int)blocks, 256, 0, stream>>>(keys, total, E, N, cursor, list);
+  HG_CHECK_LAUNCH("csr_fill_kernel");
+  out->off = off;
+  out->list = list;
+  return HG_OK;
+}

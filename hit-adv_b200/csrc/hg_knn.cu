@@ -220,7 +220,11 @@ __global__ void __launch_bounds__(256) knn_outlier_bwd_kernel(const float *__res
       float acc = 0.f;
       if (own)
         for (int t = 1; t < k1; ++t) acc += 2.0f * (v - p[(size_t)nb[t] * C + c]);
-      for (int q = p0; q < p1; ++q) acc += 2.0f * (v - p[(size_t)(l[q] / k1) * C + c]);
+      int e = -1;
+      for (int q = p0; q < p1; ++q) {  // ascending edge order, whatever order the list was filled in
+        e = hg_csr_next(l, p0, p1, e);
+        acc += 2.0f * (v - p[(size_t)(e / k1) * C + c]);
+      }
       grad[(size_t)gi * C + c] = coef * acc;
     }
   }
@@ -321,7 +325,7 @@ HG_API int hg_knn_outlier_bwd_f32(const float *pc, const int *idx, const float *
   knn_bwd_keys_kernel<<<grid_for(total, 256), 256, 0, stream>>>(idx, mask, total, k1, keys);
   HG_CHECK_LAUNCH("knn_bwd_keys_kernel");
   HgCsr csr;
-  int rc = hg_csr_build(keys, B, K * k1, K, csr_ws, hg_csr_workspace_bytes(B, K, K * k1), &csr, stream);
+  int rc = hg_csr_build_unordered(keys, B, K * k1, K, csr_ws, hg_csr_workspace_bytes(B, K, K * k1), &csr, stream);
   if (rc) return rc;
   knn_outlier_bwd_kernel<<<grid_for((long long)B * K, 256), 256, 0, stream>>>(pc, idx, mask, g, csr.off, csr.list, B, K,
                                                                               C, k1, grad_pc);

@@ -78,8 +78,9 @@ __global__ void __launch_bounds__(kThreads) knn3_kernel(const float *__restrict_
   const float *q = queries + (size_t)b * Nq * 3;
   const float *r = refs + (size_t)b * Nr * 3;
 
+  constexpr int MW = kTileC / 64;  // hit-mask words per query: one bit per candidate pair of a tile
   float a0[QT], a1[QT], a2[QT], a3[QT], thr[QT];
-  unsigned mask[QT];
+  unsigned mask[QT][MW];
   TopK<KM> top[QT];
 #pragma unroll
   for (int t = 0; t < QT; ++t) {
@@ -102,7 +103,8 @@ __global__ void __launch_bounds__(kThreads) knn3_kernel(const float *__restrict_
       a3[t] = 0.f;
     }
     thr[t] = CUDART_INF_F;
-    mask[t] = 0u;
+#pragma unroll
+    for (int w = 0; w < MW; ++w) mask[t][w] = 0u;
     top[t].init();
   }
 
@@ -135,54 +137,67 @@ __global__ void __launch_bounds__(kThreads) knn3_kernel(const float *__restrict_
     __syncthreads();
     const int npairs = (min(kTileC, Nr - base) + 1) >> 1;
 
+    // Windows between two drains.  First tile: 4,4,8,16,32,32,32 pairs so that the thresholds tighten
+    // geometrically.  Later tiles: the whole tile in one window -- hits are rare per lane but frequent per warp
+    // there, and a longer window lets several lanes insert in the same (divergent) drain iteration.
     int p0 = 0;
-    int step = (base == 0) ? 4 : 32;  // sub-tile sizes in pairs: 4,4,8,16,32,32,... then 32s
-    bool first = (base == 0);
+    int step = (base == 0) ? 4 : kTileC / 2;
     while (p0 < npairs) {
       const int cnt = min(step, npairs - p0);
       // ---- main loop: packed distances, one threshold test per (query, candidate pair) ----------------------
-#pragma unroll 2
-      for (int g = 0; g < cnt; ++g) {
-        const float4 cA = cand[2 * (p0 + g)], cB = cand[2 * (p0 + g) + 1];
-        const unsigned bit = 1u << g;
 #pragma unroll
-        for (int t = 0; t < QT; ++t) {
-          float2 d;
-          if (FORM == HG_KNN_FORM_EXPANDED) {
-            float2 tt = __fmul2_rn(make_float2(a0[t], a0[t]), make_float2(cA.x, cA.y));
-            tt = __ffma2_rn(make_float2(a1[t], a1[t]), make_float2(cA.z, cA.w), tt);
-            tt = __ffma2_rn(make_float2(a2[t], a2[t]), make_float2(cB.x, cB.y), tt);
-            const float2 s = __fadd2_rn(make_float2(cB.z, cB.w), tt);
-            d = __fadd2_rn(s, make_float2(a3[t], a3[t]));
-          } else {
-            const float2 dx = __fadd2_rn(make_float2(a0[t], a0[t]), make_float2(cA.x, cA.y));
-            const float2 dy = __fadd2_rn(make_float2(a1[t], a1[t]), make_float2(cA.z, cA.w));
-            const float2 dz = __fadd2_rn(make_float2(a2[t], a2[t]), make_float2(cB.x, cB.y));
-            d = __ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx)));
+      for (int w = 0; w < MW; ++w) {
+        const int gcnt = min(32, cnt - 32 * w);
+#pragma unroll 2
+        for (int g = 0; g < gcnt; ++g) {
+          const float4 cA = cand[2 * (p0 + 32 * w + g)], cB = cand[2 * (p0 + 32 * w + g) + 1];
+          const unsigned bit = 1u << g;
+#pragma unroll
+          for (int t = 0; t < QT; ++t) {
+            float2 d;
+            if (FORM == HG_KNN_FORM_EXPANDED) {
+              float2 tt = __fmul2_rn(make_float2(a0[t], a0[t]), make_float2(cA.x, cA.y));
+              tt = __ffma2_rn(make_float2(a1[t], a1[t]), make_float2(cA.z, cA.w), tt);
+              tt = __ffma2_rn(make_float2(a2[t], a2[t]), make_float2(cB.x, cB.y), tt);
+              const float2 s = __fadd2_rn(make_float2(cB.z, cB.w), tt);
+              d = __fadd2_rn(s, make_float2(a3[t], a3[t]));
+            } else {
+              const float2 dx = __fadd2_rn(make_float2(a0[t], a0[t]), make_float2(cA.x, cA.y));
+              const float2 dy = __fadd2_rn(make_float2(a1[t], a1[t]), make_float2(cA.z, cA.w));
+              const float2 dz = __fadd2_rn(make_float2(a2[t], a2[t]), make_float2(cB.x, cB.y));
+              d = __ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx)));
+            }
+            if (fminf(d.x, d.y) < thr[t]) mask[t][w] |= bit;
           }
-          if (fminf(d.x, d.y) < thr[t]) mask[t] |= bit;
         }
       }
       // ---- drain: each lane inserts its own hits (ascending candidate order per query) ----------------------
 #pragma unroll
       for (int t = 0; t < QT; ++t) {
-        unsigned m = mask[t];
-        while (m) {
+        while (true) {
+          int w = -1;
+          unsigned m = 0u;
+#pragma unroll
+          for (int u = MW - 1; u >= 0; --u)
+            if (mask[t][u]) {
+              w = u;
+              m = mask[t][u];
+            }
+          if (w < 0) break;
           const int g = __ffs(m) - 1;
-          m &= m - 1u;
-          const float4 cA = cand[2 * (p0 + g)], cB = cand[2 * (p0 + g) + 1];
-          const int j0 = base + 2 * (p0 + g);
+#pragma unroll
+          for (int u = 0; u < MW; ++u)
+            if (u == w) mask[t][u] = m & (m - 1u);
+          const int pp = p0 + 32 * w + g;
+          const float4 cA = cand[2 * pp], cB = cand[2 * pp + 1];
+          const int j0 = base + 2 * pp;
           top[t].push(knn_dist_exact<FORM>(a0[t], a1[t], a2[t], a3[t], cA.x, cA.z, cB.x, cB.z), j0);
           top[t].push(knn_dist_exact<FORM>(a0[t], a1[t], a2[t], a3[t], cA.y, cA.w, cB.y, cB.w), j0 + 1);
         }
-        mask[t] = 0u;
         thr[t] = top[t].v[KM - 1];
       }
       p0 += cnt;
-      if (first) {
-        if (step < 32 && p0 >= 2 * step) step *= 2;  // 4,4,8,16,32...
-        if (step >= 32) first = false;
-      }
+      if (base == 0 && step < 32 && p0 >= 2 * step) step *= 2;  // 4,4,8,16,32,32,...
     }
   }
 

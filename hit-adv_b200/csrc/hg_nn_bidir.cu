@@ -13,10 +13,10 @@
 //
 // Kernel design for sm_100a.  The inner dimension is 3, so this is FP32-pipe work, not tensor-core work.
 // Per pair the FMA pipe must execute 5 operations (FMUL, 2 FFMA, 2 FADD); they are issued as packed
-// FMUL2/FFMA2/FADD2 (two pairs per instruction, scalar x-operand broadcast by the .F32 operand form), which
+// FMUL2/FFMA2/FADD2 (two ROWS per instruction, the column operand broadcast by the .F32 operand form), which
 // halves the issue slots and leaves room for the min bookkeeping on the ALU pipe:
-//   * a lane keeps T columns (preds) resident in registers and streams the rows (gts) of the CTA's row
-//     block from shared memory (one broadcast LDS.128 per row: -2x0,-2x1,-2x2,rx);
+//   * a lane keeps T columns (preds) resident in registers (as scalars) and streams the rows (gts) of the CTA's
+//     row block from shared memory, two rows per packed instruction (broadcast LDS.128: row pairs interleaved);
 //   * column direction (min over rows): FMNMX3 over two rows at a time into T running minima; which block
 //     of kColBatch rows produced the minimum is tracked every kColBatch rows;
 //   * row direction (min over columns): FMNMX3 tree over the lane's T values, one CREDUX.MIN.F32 across the
@@ -30,7 +30,7 @@
 
 namespace {
 
-constexpr int kColBatch = 8;  // rows per column-direction tracking batch (and rescan width)
+constexpr int kColBatch = 32;  // rows per column-direction tracking batch (and rescan width of the finish kernel)
 
 struct NnParams {
   const float *gts;    // [B,N2,3]
@@ -49,14 +49,18 @@ __device__ __forceinline__ float nn_p_exact(float x0, float x1, float x2, float 
   return __fadd_rn(__fadd_rn(rx, ry), t);
 }
 
-// launch bounds: T=16 -> 12 warps per SM (3 per scheduler, <= 170 registers); T=8 -> 20 warps per SM (<= 102)
+// launch bounds: T=16 -> 12 warps per SM (3 per scheduler, <= 170 registers); T=8 -> 16 warps per SM (<= 128)
 template <int T, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, (T == 8 ? 20 : 12) / WARPS) nn_bidir_d3_kernel(NnParams p) {
-  static_assert(T % 2 == 0, "columns are processed as packed pairs");
-  constexpr int TP = T / 2;
+__global__ void __launch_bounds__(WARPS * 32, (T == 8 ? 16 : 12) / WARPS) nn_bidir_d3_kernel(NnParams p) {
   extern __shared__ float4 smem[];
-  float4 *xs = smem;                                            // [RB] (-2x0,-2x1,-2x2,rx)
-  uint4 *rowpart = reinterpret_cast<uint4 *>(smem + p.RB + 2);  // [WARPS][RB/2] (m_a,mask_a,m_b,mask_b)
+  // row block, two float4 per ROW PAIR (a,b): A = (xa0',xb0',xa1',xb1'), B = (xa2',xb2',rxa,rxb), x' = -2x;
+  // +4 entries so that the software prefetch of the last iteration stays in bounds
+  float4 *xs = smem;
+  uint4 *rowpart = reinterpret_cast<uint4 *>(smem + p.RB + 4);  // [WARPS][RB/2] (m_a,mask_a,m_b,mask_b)
+  // column-direction tracking state, one bank column per thread: running minimum at the last batch boundary and
+  // the batch that last lowered it (kept out of the register file: 2*T words per thread)
+  float *sprev = reinterpret_cast<float *>(rowpart + (size_t)WARPS * (p.RB / 2));  // [T][WARPS*32]
+  int *scid = reinterpret_cast<int *>(sprev + T * WARPS * 32);                     // [T][WARPS*32]
 
   const int b = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -65,93 +69,108 @@ __global__ void __launch_bounds__(WARPS * 32, (T == 8 ? 20 : 12) / WARPS) nn_bid
   const int r0 = blockIdx.x * p.RB;
   const bool warp_active = cgroup * 32 * T < p.N1;
 
-  // ---- stage the row block: (-2x, rx); rows past N2 get rx=+inf so they never win a minimum -----------------
+  // ---- stage the row block; rows past N2 get rx=+inf so they never win a minimum ---------------------------
   const float *gx = p.gts + (size_t)b * p.N2 * 3;
-  for (int r = threadIdx.x; r < p.RB + 2; r += WARPS * 32) {  // +2: the prefetch of the last iteration
-    const int i = r0 + r;
-    float4 v = make_float4(0.f, 0.f, 0.f, CUDART_INF_F);
-    if (i < p.N2 && r < p.RB) {
-      const float x0 = __ldg(gx + (size_t)i * 3), x1 = __ldg(gx + (size_t)i * 3 + 1), x2 = __ldg(gx + (size_t)i * 3 + 2);
-      v = make_float4(-2.0f * x0, -2.0f * x1, -2.0f * x2, hg_dot3_fma(x0, x1, x2, x0, x1, x2));
-    }
-    xs[r] = v;
-  }
-
-  // ---- this lane's T columns, packed in pairs; columns past N1 get ry=+inf ---------------------------------
-  float2 y0[TP], y1[TP], y2[TP], ry[TP];
-  const float *gy = p.preds + (size_t)b * p.N1 * 3;
-#pragma unroll
-  for (int q = 0; q < TP; ++q) {
-    float a[2][4];
+  for (int rp = threadIdx.x; rp < p.RB / 2 + 2; rp += WARPS * 32) {
+    float v[2][4];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      const int j = cbase + 2 * q + h;
-      a[h][0] = a[h][1] = a[h][2] = 0.f;
-      a[h][3] = CUDART_INF_F;
-      if (j < p.N1) {
-        a[h][0] = __ldg(gy + (size_t)j * 3);
-        a[h][1] = __ldg(gy + (size_t)j * 3 + 1);
-        a[h][2] = __ldg(gy + (size_t)j * 3 + 2);
-        a[h][3] = hg_dot3_fma(a[h][0], a[h][1], a[h][2], a[h][0], a[h][1], a[h][2]);
+      const int i = r0 + 2 * rp + h;
+      v[h][0] = v[h][1] = v[h][2] = 0.f;
+      v[h][3] = CUDART_INF_F;
+      if (i < p.N2 && 2 * rp + h < p.RB) {
+        const float x0 = __ldg(gx + (size_t)i * 3), x1 = __ldg(gx + (size_t)i * 3 + 1), x2 = __ldg(gx + (size_t)i * 3 + 2);
+        v[h][0] = -2.0f * x0;
+        v[h][1] = -2.0f * x1;
+        v[h][2] = -2.0f * x2;
+        v[h][3] = hg_dot3_fma(x0, x1, x2, x0, x1, x2);
       }
     }
-    y0[q] = make_float2(a[0][0], a[1][0]);
-    y1[q] = make_float2(a[0][1], a[1][1]);
-    y2[q] = make_float2(a[0][2], a[1][2]);
-    ry[q] = make_float2(a[0][3], a[1][3]);
+    xs[2 * rp] = make_float4(v[0][0], v[1][0], v[0][1], v[1][1]);
+    xs[2 * rp + 1] = make_float4(v[0][2], v[1][2], v[0][3], v[1][3]);
+  }
+
+  // ---- this lane's T columns as scalars; columns past N1 get ry=+inf ----------------------------------------
+  float y0[T], y1[T], y2[T], ry[T];
+  const float *gy = p.preds + (size_t)b * p.N1 * 3;
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    const int j = cbase + t;
+    y0[t] = y1[t] = y2[t] = 0.f;
+    ry[t] = CUDART_INF_F;
+    if (j < p.N1) {
+      y0[t] = __ldg(gy + (size_t)j * 3);
+      y1[t] = __ldg(gy + (size_t)j * 3 + 1);
+      y2[t] = __ldg(gy + (size_t)j * 3 + 2);
+      ry[t] = hg_dot3_fma(y0[t], y1[t], y2[t], y0[t], y1[t], y2[t]);
+    }
   }
   __syncthreads();
 
   if (warp_active) {
-    float cm[T], prev[T];
-    int cid[T];
+    float cm[T];
 #pragma unroll
     for (int t = 0; t < T; ++t) {
       cm[t] = CUDART_INF_F;
-      prev[t] = CUDART_INF_F;
-      cid[t] = r0 / kColBatch;
+      sprev[t * WARPS * 32 + threadIdx.x] = CUDART_INF_F;
+      scid[t * WARPS * 32 + threadIdx.x] = r0 / kColBatch;
     }
     uint4 *myrow = rowpart + (size_t)warp * (p.RB / 2);
 
-    float4 xa = xs[0], xb = xs[1];
+    // Packed FP32 over ROW pairs: each FMUL2/FFMA2/FADD2 produces (P[a][t], P[b][t]) for one column t.  The row
+    // operands (X0,X1,X2,RX) are shared by T consecutive instructions, which is what lets the operand-reuse
+    // cache absorb one of the two 64-bit register reads (ptxas flags ~75% of the FFMA2s; with the columns packed
+    // instead it flags ~18% and the pipe issues every 3rd cycle).  Four rows per iteration.
+    float4 xA = xs[0], xB = xs[1], xC = xs[2], xD = xs[3];
     for (int rb = 0; rb < p.RB; rb += kColBatch) {
+#pragma unroll 2
+      for (int rr = 0; rr < kColBatch; rr += 4) {
+        const int rq = (rb + rr) >> 1;  // row pair index
+        const float4 nA = xs[2 * rq + 4], nB = xs[2 * rq + 5], nC = xs[2 * rq + 6], nD = xs[2 * rq + 7];
+        const float2 X0 = make_float2(xA.x, xA.y), X1 = make_float2(xA.z, xA.w), X2 = make_float2(xB.x, xB.y),
+                     RX = make_float2(xB.z, xB.w);
+        const float2 Z0 = make_float2(xC.x, xC.y), Z1 = make_float2(xC.z, xC.w), Z2 = make_float2(xD.x, xD.y),
+                     RZ = make_float2(xD.z, xD.w);
+        float2 P[T], Q[T];
 #pragma unroll
-      for (int rr = 0; rr < kColBatch; rr += 2) {
-        const float4 xa_next = xs[rb + rr + 2], xb_next = xs[rb + rr + 3];  // software prefetch (LDS latency)
-        float2 pa[TP], pb[TP];
-#pragma unroll
-        for (int q = 0; q < TP; ++q) {
-          float2 ta = __fmul2_rn(make_float2(xa.x, xa.x), y0[q]);
-          float2 tb = __fmul2_rn(make_float2(xb.x, xb.x), y0[q]);
-          ta = __ffma2_rn(make_float2(xa.y, xa.y), y1[q], ta);
-          tb = __ffma2_rn(make_float2(xb.y, xb.y), y1[q], tb);
-          ta = __ffma2_rn(make_float2(xa.z, xa.z), y2[q], ta);
-          tb = __ffma2_rn(make_float2(xb.z, xb.z), y2[q], tb);
-          const float2 sa = __fadd2_rn(make_float2(xa.w, xa.w), ry[q]);
-          const float2 sb = __fadd2_rn(make_float2(xb.w, xb.w), ry[q]);
-          pa[q] = __fadd2_rn(sa, ta);
-          pb[q] = __fadd2_rn(sb, tb);
-          cm[2 * q] = fminf(fminf(cm[2 * q], pa[q].x), pb[q].x);
-          cm[2 * q + 1] = fminf(fminf(cm[2 * q + 1], pa[q].y), pb[q].y);
+        for (int t = 0; t < T; ++t) {
+          float2 tt = __fmul2_rn(make_float2(y0[t], y0[t]), X0);
+          float2 uu = __fmul2_rn(make_float2(y0[t], y0[t]), Z0);
+          tt = __ffma2_rn(make_float2(y1[t], y1[t]), X1, tt);
+          uu = __ffma2_rn(make_float2(y1[t], y1[t]), Z1, uu);
+          tt = __ffma2_rn(make_float2(y2[t], y2[t]), X2, tt);
+          uu = __ffma2_rn(make_float2(y2[t], y2[t]), Z2, uu);
+          P[t] = __fadd2_rn(__fadd2_rn(RX, make_float2(ry[t], ry[t])), tt);  // (rx + ry) + zz'
+          Q[t] = __fadd2_rn(__fadd2_rn(RZ, make_float2(ry[t], ry[t])), uu);
+          cm[t] = fminf(fminf(fminf(fminf(cm[t], P[t].x), P[t].y), Q[t].x), Q[t].y);  // 2 x FMNMX3
         }
-        float ma = fminf(pa[0].x, pa[0].y), mb = fminf(pb[0].x, pb[0].y);
+        float ma = fminf(P[0].x, P[1].x), mb = fminf(P[0].y, P[1].y);
+        float mc = fminf(Q[0].x, Q[1].x), md = fminf(Q[0].y, Q[1].y);
 #pragma unroll
-        for (int q = 1; q < TP; ++q) {
-          ma = fminf(fminf(ma, pa[q].x), pa[q].y);
-          mb = fminf(fminf(mb, pb[q].x), pb[q].y);
+        for (int t = 2; t < T; t += 2) {
+          ma = fminf(fminf(ma, P[t].x), P[t + 1].x);
+          mb = fminf(fminf(mb, P[t].y), P[t + 1].y);
+          mc = fminf(fminf(mc, Q[t].x), Q[t + 1].x);
+          md = fminf(fminf(md, Q[t].y), Q[t + 1].y);
         }
         const float wa = hg_warp_min_f32(ma), wb = hg_warp_min_f32(mb);
-        const unsigned ka = __ballot_sync(0xffffffffu, ma == wa);
-        const unsigned kb = __ballot_sync(0xffffffffu, mb == wb);
-        if (lane == 0) myrow[(rb + rr) >> 1] = make_uint4(__float_as_uint(wa), ka, __float_as_uint(wb), kb);
-        xa = xa_next;
-        xb = xb_next;
+        const float wc = hg_warp_min_f32(mc), wd = hg_warp_min_f32(md);
+        const unsigned ka = __ballot_sync(0xffffffffu, ma == wa), kb = __ballot_sync(0xffffffffu, mb == wb);
+        const unsigned kc = __ballot_sync(0xffffffffu, mc == wc), kd = __ballot_sync(0xffffffffu, md == wd);
+        if (lane == 0) {
+          myrow[rq] = make_uint4(__float_as_uint(wa), ka, __float_as_uint(wb), kb);
+          myrow[rq + 1] = make_uint4(__float_as_uint(wc), kc, __float_as_uint(wd), kd);
+        }
+        xA = nA;
+        xB = nB;
+        xC = nC;
+        xD = nD;
       }
       const int batch = (r0 + rb) / kColBatch;
 #pragma unroll
       for (int t = 0; t < T; ++t) {
-        if (cm[t] < prev[t]) cid[t] = batch;
-        prev[t] = cm[t];
+        if (cm[t] < sprev[t * WARPS * 32 + threadIdx.x]) scid[t * WARPS * 32 + threadIdx.x] = batch;
+        sprev[t * WARPS * 32 + threadIdx.x] = cm[t];
       }
     }
     // column direction: merge with the other row blocks
@@ -159,7 +178,8 @@ __global__ void __launch_bounds__(WARPS * 32, (T == 8 ? 20 : 12) / WARPS) nn_bid
 #pragma unroll
     for (int t = 0; t < T; ++t) {
       const int j = cbase + t;
-      if (j < p.N1) atomicMin(cr + j, ((unsigned long long)hg_ord(cm[t]) << 32) | (unsigned)cid[t]);
+      if (j < p.N1)
+        atomicMin(cr + j, ((unsigned long long)hg_ord(cm[t]) << 32) | (unsigned)scid[t * WARPS * 32 + threadIdx.x]);
     }
   }
   __syncthreads();
@@ -398,8 +418,9 @@ __global__ void __launch_bounds__(256) set_loss_bwd_kernel(
       float acc = 0.f;
       if (cs != 0.f) acc = cs * (2.0f * (v - po[(size_t)a * D + c]));
       float sc = 0.f;
-      for (int q = p0; q < p1; ++q) {
-        const int o = lst[q];
+      int o = -1;
+      for (int q = p0; q < p1; ++q) {  // ascending source index, whatever order the list was filled in
+        o = hg_csr_next(lst, p0, p1, o);
         if (mode == HG_MODE_CHAMFER || o == hdo) sc += 2.0f * (v - po[(size_t)o * D + c]);
       }
       grad_self[((size_t)b * Ns + s) * D + c] = acc + co * sc;
@@ -411,7 +432,8 @@ template <int T, int WARPS>
 int launch_main(const NnParams &p, int B, cudaStream_t stream) {
   const int ncg = (p.N1 + 32 * T - 1) / (32 * T);
   dim3 grid((p.N2 + p.RB - 1) / p.RB, (ncg + WARPS - 1) / WARPS, B);
-  const size_t smem = (size_t)(p.RB + 2) * sizeof(float4) + (size_t)WARPS * (p.RB / 2) * sizeof(uint4);
+  const size_t smem = (size_t)(p.RB + 4) * sizeof(float4) + (size_t)WARPS * (p.RB / 2) * sizeof(uint4) +
+                      (size_t)2 * T * WARPS * 32 * sizeof(float);
   const bool prof = hg_prof_begin(HG_PROF_NN_BIDIR, stream);
   nn_bidir_d3_kernel<T, WARPS><<<grid, WARPS * 32, smem, stream>>>(p);
   hg_prof_end(HG_PROF_NN_BIDIR, stream, prof);
@@ -481,8 +503,8 @@ HG_API int hg_nn_bidir_f32(const float *gts, const float *preds, int B, int N2, 
   if (!RB) {
     const int ncg_ = (N1 + 32 * T - 1) / (32 * T);
     const int wpc = (ncg_ >= 4 && ncg_ % 4 == 0) ? 4 : (ncg_ >= 2 ? 2 : 1);
-    RB = 256;
-    while (RB > 32) {
+    RB = 512;
+    while (RB > kColBatch) {
       const long long ctas = (long long)B * ((N2 + RB - 1) / RB) * ((ncg_ + wpc - 1) / wpc);
       if (ctas * wpc >= (long long)hg_sm_count() * 12 * 4) break;  // >= 4 waves of 12 warps per SM
       RB >>= 1;
@@ -553,7 +575,7 @@ HG_API int hg_set_loss_bwd_f32(const float *gts, const float *preds, const int *
              "set_loss_bwd: workspace too small");
   // preds (adv, "y"): gathers through arg1 (loss1), receives scatter from arg2 (loss2)
   HgCsr rev2;
-  int rc = hg_csr_build(arg2, B, N2, N1, workspace, hg_csr_workspace_bytes(B, N1, N2), &rev2, stream);
+  int rc = hg_csr_build_unordered(arg2, B, N2, N1, workspace, hg_csr_workspace_bytes(B, N1, N2), &rev2, stream);
   if (rc) return rc;
   const long long tp = (long long)B * N1;
   set_loss_bwd_kernel<<<grid_for(tp, 256), 256, 0, stream>>>(preds, gts, arg1, rev2.off, rev2.list, g1, g2, hd_arg1,
@@ -562,7 +584,7 @@ HG_API int hg_set_loss_bwd_f32(const float *gts, const float *preds, const int *
   if (grad_gts) {
     HgCsr rev1;
     void *ws2 = (char *)workspace + hg_csr_workspace_bytes(B, N1, N2);
-    rc = hg_csr_build(arg1, B, N1, N2, ws2, hg_csr_workspace_bytes(B, N2, N1), &rev1, stream);
+    rc = hg_csr_build_unordered(arg1, B, N1, N2, ws2, hg_csr_workspace_bytes(B, N2, N1), &rev1, stream);
     if (rc) return rc;
     const long long tg = (long long)B * N2;
     set_loss_bwd_kernel<<<grid_for(tg, 256), 256, 0, stream>>>(gts, preds, arg2, rev1.off, rev1.list, g2, g1, hd_arg2,

@@ -33,19 +33,70 @@ int ref_opt_n_threads(int work_size) {
 }
 
 // ---- gather / group (sampling_gpu.cu:8-20, group_points_gpu.cu:8-28) ---------------------------------------
-// out[b,c,e] = points[b,c,idx[b,e]],  e over the flattened index tensor (m, or npoints*nsample)
+// out[b,c,e] = points[b,c,idx[b,e]],  e over the flattened index tensor (m, or npoints*nsample).
+// HBM-bound on the output write: one CTA row per (b,c) plane, four consecutive e per thread (int4 index load,
+// four gathers that hit L1/L2 -- a plane of n floats is a few KB --, one float4 store), no integer division.
+// SMEM: the (b,c) source plane (n floats) is staged in shared memory first -- random 4-byte gathers from L1 cost one
+// wavefront per distinct line and cap the kernel near 2 TB/s; from shared memory they cost a few bank cycles.
+template <bool VEC4, bool SMEM>
 __global__ void __launch_bounds__(256) gather_channel_major_kernel(const float *__restrict__ points,
-                                                                   const int *__restrict__ idx, int b, int c, int n,
-                                                                   int E, float *__restrict__ out) {
-  const long long total = (long long)b * c * E;
-  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total;
-       g += (long long)gridDim.x * blockDim.x) {
-    const int e = (int)(g % E);
-    const long long bc = g / E;
+                                                                   const int *__restrict__ idx, int c, int n, int E,
+                                                                   long long planes, float *__restrict__ out) {
+  extern __shared__ float plane[];
+  for (long long bc = blockIdx.y; bc < planes; bc += gridDim.y) {
     const int bi = (int)(bc / c);
-    const int a = __ldg(idx + (size_t)bi * E + e);
-    out[g] = __ldg(points + (size_t)bc * n + a);
+    const float *src = points + (size_t)bc * n;
+    const int *id = idx + (size_t)bi * E;
+    float *dst = out + (size_t)bc * E;
+    if (SMEM) {
+      __syncthreads();
+      for (int k = threadIdx.x; k < n; k += 256) plane[k] = __ldg(src + k);
+      __syncthreads();
+    }
+    const float *tab = SMEM ? plane : src;
+    if (VEC4) {
+      for (int e = (blockIdx.x * 256 + threadIdx.x) * 4; e < E; e += gridDim.x * 1024) {
+        const int4 a = *reinterpret_cast<const int4 *>(id + e);
+        float4 v;
+        v.x = tab[a.x];
+        v.y = tab[a.y];
+        v.z = tab[a.z];
+        v.w = tab[a.w];
+        __stcs(reinterpret_cast<float4 *>(dst + e), v);  // streaming store: the output is not re-read here
+      }
+    } else {
+      for (int e = blockIdx.x * 256 + threadIdx.x; e < E; e += gridDim.x * 256) dst[e] = tab[__ldg(id + e)];
+    }
   }
+}
+
+int launch_gather(const float *points, const int *idx, int b, int c, int n, int E, float *out, cudaStream_t stream,
+                  int prof_tag) {
+  const long long planes = (long long)b * c;
+  const bool vec = (E % 4 == 0) && ((reinterpret_cast<uintptr_t>(idx) | reinterpret_cast<uintptr_t>(out)) % 16 == 0);
+  const int per_block = vec ? 1024 : 256;
+  // stage the plane when it is re-used enough (E >= n) and fits; then one CTA column per plane
+  const bool use_smem = (size_t)n * sizeof(float) <= 96 * 1024 && E >= n;
+  int gx = (E + per_block - 1) / per_block;
+  const int gx_cap = use_smem ? 4 : 64;
+  if (gx > gx_cap) gx = gx_cap;
+  const int gy = (int)(planes < 65535 ? planes : 65535);
+  const size_t smem = use_smem ? (size_t)n * sizeof(float) : 0;
+  const bool prof = prof_tag >= 0 ? hg_prof_begin(prof_tag, stream) : false;
+#define HG_GATHER_LAUNCH(V, S)                                                                                     \
+  do {                                                                                                             \
+    if (smem > 48 * 1024)                                                                                          \
+      cudaFuncSetAttribute(gather_channel_major_kernel<V, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    gather_channel_major_kernel<V, S><<<dim3(gx, gy), 256, smem, stream>>>(points, idx, c, n, E, planes, out);     \
+  } while (0)
+  if (vec && use_smem) HG_GATHER_LAUNCH(true, true);
+  else if (vec) HG_GATHER_LAUNCH(true, false);
+  else if (use_smem) HG_GATHER_LAUNCH(false, true);
+  else HG_GATHER_LAUNCH(false, false);
+#undef HG_GATHER_LAUNCH
+  hg_prof_end(prof_tag, stream, prof);
+  HG_CHECK_LAUNCH("gather_channel_major_kernel");
+  return HG_OK;
 }
 
 // grad_points[b,c,key] = sum over the edges e of key, ascending e, of src[b,c,e / DIV] * (w ? w[b,e] : 1)
@@ -313,10 +364,7 @@ HG_API int hg_p2_gather_points(int b, int c, int n, int npoints, const float *po
                                hgStream stream_) {
   HG_REQUIRE(points && idx && out, HG_E_BADARG, "gather_points: null pointer");
   HG_REQUIRE(b > 0 && c > 0 && n > 0 && npoints > 0, HG_E_BADARG, "gather_points: sizes must be positive");
-  const long long total = (long long)b * c * npoints;
-  gather_channel_major_kernel<<<grid_for(total, 256), 256, 0, hg_stream(stream_)>>>(points, idx, b, c, n, npoints, out);
-  HG_CHECK_LAUNCH("gather_points");
-  return HG_OK;
+  return launch_gather(points, idx, b, c, n, npoints, out, hg_stream(stream_), -1);
 }
 
 HG_API size_t hg_p2_scatter_workspace_bytes(int b, int n, int nedges) {
@@ -372,13 +420,7 @@ HG_API int hg_p2_group_points(int b, int c, int n, int npoints, int nsample, con
                               float *out, hgStream stream_) {
   HG_REQUIRE(points && idx && out, HG_E_BADARG, "group_points: null pointer");
   HG_REQUIRE(b > 0 && c > 0 && n > 0 && npoints > 0 && nsample > 0, HG_E_BADARG, "group_points: sizes must be positive");
-  const long long total = (long long)b * c * npoints * nsample;
-  const bool prof = hg_prof_begin(HG_PROF_GROUP, hg_stream(stream_));
-  gather_channel_major_kernel<<<grid_for(total, 256), 256, 0, hg_stream(stream_)>>>(points, idx, b, c, n,
-                                                                                     npoints * nsample, out);
-  hg_prof_end(HG_PROF_GROUP, hg_stream(stream_), prof);
-  HG_CHECK_LAUNCH("group_points");
-  return HG_OK;
+  return launch_gather(points, idx, b, c, n, npoints * nsample, out, hg_stream(stream_), HG_PROF_GROUP);
 }
 
 HG_API int hg_p2_group_points_grad(int b, int c, int n, int npoints, int nsample, const float *grad_out,

@@ -11,6 +11,8 @@ meaning and error behaviour), calling hand-written CUDA kernels through the C AB
     hitgeom.pytorch3d_ops  knn_points, knn_gather                                      (pytorch3d.ops)
     hitgeom.install()      registers the above under the names the unmodified reference imports
     hitgeom.sharding       instance-sharded multi-GPU driver (one process per GPU, NCCL all-gather at the end)
+    hitgeom.hit_adv        HiT_ADV attacker with the fused deformation kernel and on-device bookkeeping
+                           (ShapeAttack/HiT_ADV.py; SURVEY.md 8f "next" rows #1, #2)
 
 There is no CPU path: importing works anywhere (so the build can be checked without a GPU), but every
 operator raises unless its tensors live on a CUDA device and libhitgeom.so is present.
@@ -26,6 +28,6 @@ def __getattr__(name):
     import importlib
 
     if name in ("set_distance", "dist_utils", "pointnet2_ops", "model_seams", "pytorch3d_ops", "functional",
-                "sharding"):
+                "sharding", "hit_adv"):
         return importlib.import_module(f".{name}", __name__)
     raise AttributeError(name)

@@ -240,6 +240,42 @@ class IndexPointsFn(torch.autograd.Function):
         return grad, None
 
 
+class DeformFn(torch.autograd.Function):
+    """Fused HiT-ADV deformation (HiT_ADV.py:168-175,298-304): (ori [B,3,K], centers [B,3,J], perturb [B,J,3],
+    delta [B,J]) -> deformed cloud [B,3,K]; differentiable in perturb and delta."""
+
+    @staticmethod
+    def forward(ctx, ori, centers, perturb, delta):
+        ori_c, cen_c = ori.detach().contiguous(), centers.detach().contiguous()
+        per_c, del_c = perturb.detach().contiguous(), delta.detach().contiguous()
+        for t, name in ((ori_c, "ori"), (cen_c, "centers"), (per_c, "perturb"), (del_c, "delta")):
+            require(t, name)
+        B, _, K = ori_c.shape
+        J = cen_c.shape[2]
+        out = torch.empty_like(ori_c)
+        deno = torch.empty((B, K), dtype=torch.float32, device=ori_c.device)
+        check(lib().hg_hitadv_deform_fwd_f32(ptr(ori_c), ptr(cen_c), ptr(per_c), ptr(del_c), B, K, J, ptr(out), ptr(deno),
+                                             stream_ptr()), "hg_hitadv_deform_fwd_f32")
+        ctx.saved = (ori_c, cen_c, per_c, del_c, out, deno)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        ori_c, cen_c, per_c, del_c, out, deno = ctx.saved
+        B, _, K = ori_c.shape
+        J = cen_c.shape[2]
+        g = grad_out.to(torch.float32).contiguous()
+        gp = torch.empty_like(per_c)
+        gd = torch.empty_like(del_c)
+        check(lib().hg_hitadv_deform_bwd_f32(ptr(ori_c), ptr(cen_c), ptr(per_c), ptr(del_c), ptr(out), ptr(deno), ptr(g),
+                                             B, K, J, ptr(gp), ptr(gd), stream_ptr()), "hg_hitadv_deform_bwd_f32")
+        return None, None, gp, gd
+
+
+def hitadv_deform(ori, centers, perturb, delta):
+    return DeformFn.apply(ori, centers, perturb, delta)
+
+
 def tune_nn_bidir(T=0, RB=0):
     """Benchmark-only override of the nn_bidir tile shape (0 = automatic)."""
     lib().hg_nn_bidir_tune(int(T), int(RB))

@@ -162,6 +162,18 @@ int hg_p2_three_interpolate_grad(int b, int c, int n, int m, const float *grad_o
                                  const float *weight, float *grad_points, void *workspace, size_t workspace_bytes,
                                  hgStream stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * "Next" row 8f#1: the fused HiT-ADV deformation, ShapeAttack/HiT_ADV.py:168-175 + kernel_density :298-304.
+ *   ori [B,3,K], centers [B,3,J] (channel-first, as the attack holds them), perturb [B,J,3], delta [B,J]
+ *   out [B,3,K] = sum_j (x + p_j) w_j / sum_j w_j,  w_j = exp(-||x - c_j|| / (2 delta_j^2));  deno [B,K] = sum_j w_j
+ * The backward returns the gradients w.r.t. the two optimised tensors (ori / centers are constants in the attack).
+ * ------------------------------------------------------------------------------------------------------- */
+int hg_hitadv_deform_fwd_f32(const float *ori, const float *centers, const float *perturb, const float *delta, int B,
+                             int K, int J, float *out, float *deno, hgStream stream);
+int hg_hitadv_deform_bwd_f32(const float *ori, const float *centers, const float *perturb, const float *delta,
+                             const float *out, const float *deno, const float *grad_out, int B, int K, int J,
+                             float *grad_perturb, float *grad_delta, hgStream stream);
+
 #ifdef __cplusplus
 }
 #endif

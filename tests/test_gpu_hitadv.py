@@ -1,0 +1,114 @@
+"""The fused HiT-ADV deformation kernels and the B200-native attack loop against (a) the oracle's torch restatement
+of the reference loop and (b) the golden output of the UNMODIFIED reference class (tests/golden/hitadv_ref.npz,
+produced on CPU).  Floating point: 1e-5 relative for the deformation and its gradients; the full attack (12 Adam
+steps through a network, CPU vs GPU transcendental and reduction rounding) within 2e-3 absolute on coordinates of
+magnitude 1, with identical discrete outcomes (success count)."""
+import numpy as np
+import pytest
+import torch
+
+from util_inputs import clouds, normwise
+from util_models import TinyPointNet
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("B,K,J", [(3, 256, 8), (2, 1024, 192), (4, 100, 33)])
+def test_deform_fwd_bwd_vs_torch_restatement(B, K, J):
+    from hitgeom import functional as F
+    from oracle import hitadv_port as hp
+
+    g = torch.Generator().manual_seed(B * 1000 + J)
+    ori = torch.from_numpy(clouds(B, K, 5 + K)).transpose(1, 2).contiguous()
+    sel = torch.stack([torch.randperm(K, generator=g)[:J] for _ in range(B)])
+    centers = torch.gather(ori, 2, sel[:, None, :].expand(-1, 3, -1)).contiguous()
+    perturb = (torch.rand(B, J, 3, generator=g) - 0.5) * 0.6
+    delta = 0.1 + torch.rand(B, J, generator=g) * 1.1
+    w = torch.randn(B, 3, K, generator=g)
+    # reference path (torch, float64 for a tight yardstick and float32 as the reference actually runs)
+    outs = {}
+    for dt in (torch.float64, torch.float32):
+        p, d = perturb.to(dt).clone().requires_grad_(), delta.to(dt).clone().requires_grad_()
+        out = hp.deform(ori.to(dt), p, hp.kernel_density(centers.to(dt), ori.to(dt), d))
+        (out * w.to(dt)).sum().backward()
+        outs[dt] = (out.detach(), p.grad, d.grad)
+    p, d = perturb.clone().cuda().requires_grad_(), delta.clone().cuda().requires_grad_()
+    out = F.hitadv_deform(ori.cuda(), centers.cuda(), p, d)
+    (out * w.cuda()).sum().backward()
+    ref_o, ref_p, ref_d = (t.double().numpy() for t in outs[torch.float64])
+    assert np.abs(out.detach().cpu().numpy() - ref_o).max() <= 1e-5 * np.abs(ref_o).max()
+    assert normwise(p.grad.cpu().numpy(), ref_p) < 1e-4  # FP32 sum over K terms vs float64
+    assert normwise(d.grad.cpu().numpy(), ref_d) < 1e-4
+    # and no further from float64 than the reference's own FP32 path is (x4 slack)
+    e32 = normwise(outs[torch.float32][1].numpy().astype(np.float64), ref_p)
+    assert normwise(p.grad.cpu().numpy(), ref_p) <= max(4 * e32, 2e-6)
+
+
+def test_attack_loop_matches_reference_golden(golden):
+    from hitgeom.hit_adv import HiT_ADV, UntargetedLogitsAdvLoss
+
+    g = golden("hitadv_ref")
+    HP = {k[3:]: g[k].item() for k in g.files if k.startswith("hp_")}
+    kappa = HP.pop("kappa")
+    for k in ("binary_step", "num_iter", "curv_loss_knn", "central_num", "total_central_num"):
+        HP[k] = int(HP[k])
+    model = TinyPointNet(40, seed=int(g["model_seed"]))
+    attacker = HiT_ADV(model, UntargetedLogitsAdvLoss(kappa=kappa), clip_func=None, **HP)
+    torch.manual_seed(int(g["seed"]))
+    best, succ = attacker.attack(torch.from_numpy(g["data"]), torch.from_numpy(g["target"]))
+    assert best.dtype == np.float64 and best.shape == g["best"].shape
+    assert int(succ) == int(g["success"])
+    assert attacker.iterations_run == HP["binary_step"] * HP["num_iter"]
+    assert np.abs(best - g["best"]).max() < 2e-3
+
+
+def test_setup_and_one_iteration_vs_port():
+    """Centre selection (exact) and one iteration's loss + parameter gradients (1e-4) against the oracle's
+    restatement on the CPU, from identical states.  (Whole trajectories cannot be compared beyond ~10 Adam steps:
+    Adam turns sign noise of near-zero gradient components into lr-sized steps.)"""
+    from hitgeom.dist_utils import ChamferDist
+    from hitgeom.hit_adv import HiT_ADV, UntargetedLogitsAdvLoss
+    from oracle import hitadv_port as hp
+
+    B, K = 6, 512
+    pts = clouds(B, K, 99)
+    nrm = np.random.default_rng(1).standard_normal((B, K, 3)).astype(np.float32)
+    nrm /= np.linalg.norm(nrm, axis=-1, keepdims=True)
+    data = torch.from_numpy(np.concatenate([pts, nrm], -1))
+    model_cpu, model = TinyPointNet(40, seed=5), TinyPointNet(40, seed=5)
+    with torch.no_grad():
+        target = model_cpu(data[:, :, :3].transpose(1, 2)).argmax(1)
+    HP = dict(attack_lr=1e-2, init_weight=10.0, max_weight=80.0, binary_step=3, num_iter=10, cd_weight=1e-4, curv_weight=0,
+              ker_weight=1.0, hide_weight=1.0, curv_loss_knn=16, central_num=24, total_central_num=48, max_sigm=1.2,
+              min_sigm=0.1, budget=0.55, alpha=1)
+    att = HiT_ADV(model, UntargetedLogitsAdvLoss(kappa=30.0), clip_func=None, **HP)
+    ori = data[:, :, :3].transpose(1, 2).contiguous()
+    normal = data[:, :, 3:].transpose(1, 2).contiguous()
+    torch.manual_seed(21)
+    _, central_ref, cks_ref = hp.setup(model_cpu, ori, normal, target, dict(HP, kappa=30.0))
+    torch.manual_seed(21)
+    central, cks = att._select_centres(ori.cuda(), normal.cuda(), target.cuda())
+    assert np.array_equal(central.cpu().numpy(), central_ref.numpy())
+    np.testing.assert_allclose(cks.cpu().numpy(), cks_ref.numpy(), rtol=2e-4, atol=1e-6)
+    g = torch.Generator().manual_seed(3)
+    J = HP["central_num"]
+    perturb = (torch.rand(B, J, 3, generator=g) - 0.3) * 0.5
+    delta = 0.1 + torch.rand(B, J, generator=g) * 1.1
+    scale = torch.linspace(5.0, 40.0, B)
+    # reference-style iteration on the CPU
+    p, d = perturb.clone().requires_grad_(), delta.clone().requires_grad_()
+    tmp = hp.deform(ori, p, hp.kernel_density(central_ref, ori, d))
+    logits = model_cpu(tmp)
+    dist_loss = (hp.chamfer_channel_first(tmp, ori, torch.ones(B) * 1e-4) + hp.transformation_loss(p, d, J)
+                 + hp.curv_std_loss(d, cks_ref, 1.2, 0.1).mean())
+    loss_ref = hp.untargeted_logits_loss(logits, target, 30.0) + scale * dist_loss
+    loss_ref.mean().backward()
+    # native iteration on the GPU
+    pg, dg = perturb.clone().cuda().requires_grad_(), delta.clone().cuda().requires_grad_()
+    loss, tmp_g, _ = att._iteration_loss(ori.cuda(), central, cks, pg, dg, target.cuda(), scale.cuda(), ChamferDist(),
+                                         torch.ones(B, device="cuda") * 1e-4)
+    loss.mean().backward()
+    np.testing.assert_allclose(tmp_g.detach().cpu().numpy(), tmp.detach().numpy(), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(loss.detach().cpu().numpy(), loss_ref.detach().numpy(), rtol=1e-4)
+    assert normwise(pg.grad.cpu().numpy(), p.grad.numpy()) < 1e-3
+    assert normwise(dg.grad.cpu().numpy(), d.grad.numpy()) < 1e-3

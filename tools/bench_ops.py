@@ -1,0 +1,124 @@
+"""Per-operator numbers for the pointnet2_ops / seam kernels: device time, HBM GB/s against
+the measured copy bandwidth (gather / group are HBM-bound), rounds/s for FPS -- next to the reference's OWN CUDA
+kernels (oracle/_ref/_ext_ref.so: the unmodified sources compiled for sm_100) timed on the same GPU, same inputs.
+Results: gpurun_out/bench_ops.json (summarised under profiles/)."""
+import importlib.util
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "hit-adv_b200"), os.path.join(ROOT, "tests")):
+    sys.path.insert(0, p)
+import torch  # noqa: E402
+
+from hitgeom import functional as F  # noqa: E402
+from hitgeom import model_seams as ms  # noqa: E402
+from hitgeom.pointnet2_ops import _ext  # noqa: E402
+
+
+def load_ref():
+    so = os.path.join(ROOT, "oracle", "_ref", "_ext_ref.so")
+    if not os.path.exists(so):
+        return None
+    spec = importlib.util.spec_from_file_location("_ext_ref", so)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def timeit(fn, iters=20, flush=None):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    tot = 0.0
+    for _ in range(iters):
+        if flush is not None:
+            flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        tot += a.elapsed_time(b)
+    return tot / iters
+
+
+def main():
+    ref = load_ref()
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    res = []
+
+    def row(name, ms_new, ms_ref, bytes_alg=None, extra=None):
+        r = {"op": name, "ms": ms_new, "ref_ms": ms_ref, "speedup_vs_ref_cuda": (ms_ref / ms_new) if ms_ref else None}
+        if bytes_alg:
+            r["alg_bytes"] = bytes_alg
+            r["gbs"] = bytes_alg / ms_new / 1e6
+            r["hbm_frac_of_measured"] = r["gbs"] / hbm
+        if extra:
+            r.update(extra)
+        res.append(r)
+        print(r, flush=True)
+
+    torch.manual_seed(0)
+    # ---- config 3 shapes: PointNet++ SSG, batch 64 x 1024 ----------------------------------------------------
+    B, N = 64, 1024
+    xyz = torch.randn(B, N, 3, device="cuda")
+    xyz = xyz / xyz.norm(dim=-1).amax(dim=1)[:, None, None]
+    for npoint in (512, 128, 51):
+        t_new = timeit(lambda: _ext.furthest_point_sampling(xyz, npoint))
+        t_ref = timeit(lambda: ref.furthest_point_sampling(xyz, npoint)) if ref else None
+        row(f"furthest_point_sampling B={B} N={N} npoint={npoint}", t_new, t_ref, extra={"rounds_per_s": B * npoint / t_new * 1e3})
+    start = torch.randint(0, N, (B,), device="cuda")
+    row(f"torch-semantics FPS B={B} N={N} npoint=512", timeit(lambda: F.fps_torch(xyz, 512, start)), None)
+    fps = _ext.furthest_point_sampling(xyz, 512)
+    new_xyz = _ext.gather_points(xyz.transpose(1, 2).contiguous(), fps).transpose(1, 2).contiguous()
+    for (r, ns) in ((0.2, 32), (0.4, 64)):
+        t_new = timeit(lambda: _ext.ball_query(new_xyz, xyz, r, ns))
+        t_ref = timeit(lambda: ref.ball_query(new_xyz, xyz, r, ns)) if ref else None
+        row(f"ball_query B={B} N={N} S=512 r={r} ns={ns}", t_new, t_ref, bytes_alg=B * (N + 512) * 12 + B * 512 * ns * 4)
+    row(f"torch-semantics query_ball_point B={B} N={N} S=512 r=0.2 ns=32", timeit(lambda: ms.query_ball_point(0.2, 32, xyz, new_xyz)), None)
+    for (C, S, ns, n) in ((3, 512, 32, 1024), (131, 128, 64, 512), (64, 512, 32, 1024)):
+        pts = torch.randn(B, C, n, device="cuda")
+        idx = torch.randint(0, n, (B, S, ns), device="cuda", dtype=torch.int32)
+        by = 4 * B * (C * n + S * ns + C * S * ns)
+        t_new = timeit(lambda: _ext.group_points(pts, idx), flush=flush)
+        t_ref = timeit(lambda: ref.group_points(pts, idx), flush=flush) if ref else None
+        row(f"group_points B={B} C={C} n={n} S={S} ns={ns}", t_new, t_ref, bytes_alg=by)
+        go = torch.randn(B, C, S, ns, device="cuda")
+        t_new = timeit(lambda: _ext.group_points_grad(go, idx, n), flush=flush)
+        t_ref = timeit(lambda: ref.group_points_grad(go, idx, n), flush=flush) if ref else None
+        row(f"group_points_grad B={B} C={C} n={n} S={S} ns={ns}", t_new, t_ref, bytes_alg=by + 4 * B * C * n)
+    unknown, known = xyz, new_xyz[:, :128].contiguous()
+    t_new = timeit(lambda: _ext.three_nn(unknown, known))
+    t_ref = timeit(lambda: ref.three_nn(unknown, known)) if ref else None
+    row(f"three_nn B={B} n={N} m=128", t_new, t_ref)
+    d2, i3 = _ext.three_nn(unknown, known)
+    w = torch.rand(B, N, 3, device="cuda")
+    feats = torch.randn(B, 256, 128, device="cuda")
+    t_new = timeit(lambda: _ext.three_interpolate(feats, i3, w), flush=flush)
+    t_ref = timeit(lambda: ref.three_interpolate(feats, i3, w), flush=flush) if ref else None
+    row(f"three_interpolate B={B} c=256 m=128 n={N}", t_new, t_ref, bytes_alg=4 * B * (256 * 128 + 6 * N + 256 * N))
+    # ---- config 4 shapes: DGCNN k=20, batch 32 x 1024 ----------------------------------------------------------
+    for C in (3, 64, 128):
+        x = torch.randn(32, C, 1024, device="cuda")
+        t_new = timeit(lambda: ms.knn(x, 20))
+
+        def ref_knn():  # the reference's torch program for DGCNN knn (model/dgcnn_cls.py:7-13) on the same GPU
+            inner = -2 * torch.matmul(x.transpose(2, 1), x)
+            xx = torch.sum(x ** 2, dim=1, keepdim=True)
+            return (-xx - inner - xx.transpose(2, 1)).topk(k=20, dim=-1)[1]
+
+        row(f"DGCNN knn B=32 C={C} N=1024 k=20", t_new, timeit(ref_knn), extra={"pair_evals_per_s": 32 * 1024 * 1024 / t_new * 1e3, "ref": "torch matmul+topk on the same GPU"})
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    json.dump({"hbm_peak_gbs_measured": hbm, "results": res}, open(os.path.join(ROOT, "gpurun_out", "bench_ops.json"), "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
