@@ -41,7 +41,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="hitgeom", choices=["hitgeom", "reference"])
-    ap.add_argument("--workload", default="c5shard", choices=["c5shard", "c1"])
+    ap.add_argument("--workload", default="c5shard", choices=["c5shard", "c1", "hitadv"])
     ap.add_argument("--clouds", type=int, default=0, help="clouds per GPU (default: workload's)")
     ap.add_argument("--points", type=int, default=0, help="points per cloud (default: workload's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -364,9 +364,140 @@ def main_hitgeom(args):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------------------------------
+# BASELINE config 2: the HiT-ADV attack loop on 1024-point clouds against a random-init PointNet (eval.py defaults:
+# batch 256, central_num 192, total_central_num 256, curv_loss_knn 16, budget 0.55, cd/ker/hide = 1e-4/1/1, kappa 30)
+# A "step" = one inner attack iteration over the batch (deformation -> victim fwd/bwd -> losses -> Adam ->
+# best-result bookkeeping).  value = cloud-iterations per second.
+# ------------------------------------------------------------------------------------------------------------
+HITADV_METRIC = "HiT-ADV attack cloud-iterations/sec"
+HITADV_HP = dict(attack_lr=1e-2, init_weight=10.0, max_weight=80.0, cd_weight=1e-4, curv_weight=0, ker_weight=1.0,
+                 hide_weight=1.0, curv_loss_knn=16, central_num=192, total_central_num=256, max_sigm=1.2, min_sigm=0.1,
+                 budget=0.55, alpha=1)
+
+
+def hitadv_inputs(B, K, seed):
+    ori, _ = make_clouds(B, K, seed)
+    rng = np.random.default_rng(seed + 1)
+    nrm = rng.standard_normal((B, K, 3)).astype(np.float32)
+    nrm /= np.linalg.norm(nrm, axis=-1, keepdims=True)
+    data = torch.from_numpy(np.concatenate([ori, nrm], axis=-1))
+    target = torch.from_numpy(rng.integers(0, 40, B))
+    return data, target
+
+
+def hitadv_cpu(B, K, iters):
+    """The reference loop (oracle/hitadv_port.py, bit-identical to the reference class here) on the host cores."""
+    from oracle import hitadv_port as hp
+    from util_models import PointNetCls
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    data, target = hitadv_inputs(B, K, 4321)
+    model = PointNetCls(40, seed=0)
+    torch.manual_seed(0)
+    t0 = time.time()
+    hp.attack(model, data, target, dict(HITADV_HP, kappa=30.0, binary_step=1, num_iter=iters))
+    dt = time.time() - t0
+    return {"value": B * iters / dt, "unit": "cloud-iterations/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": f"batch of {B} clouds x {K} points, {iters} iterations (incl. one-off setup)", "ms_per_step": dt / iters * 1e3}
+
+
+def main_hitadv(args):
+    from util_models import PointNetCls
+
+    B, K = (args.clouds or 256), (args.points or 1024)
+    name = f"C2: HiT-ADV attack loop, batch {B} x {K} points, random-init PointNet victim, eval.py defaults"
+    if args.impl == "reference":
+        if int(os.environ.get("RANK", "0")) != 0:
+            return
+        r = hitadv_cpu(8, K, max(5, args.steps))
+        line = {"impl": "reference", "metric": HITADV_METRIC, "value": r["value"], "unit": r["unit"], "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": name},
+                "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": r["value"], "unit": r["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+        print(json.dumps(line), flush=True)
+        return
+    from hitgeom import _lib, sharding
+    from hitgeom.hit_adv import HiT_ADV, UntargetedLogitsAdvLoss
+
+    rank, world, local = sharding.init()
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    data, target = hitadv_inputs(B, K, 1234 + rank)
+    model = PointNetCls(40, seed=0).to(dev)
+    steps = max(5, args.steps)
+
+    def run(n_iter):
+        att = HiT_ADV(model, UntargetedLogitsAdvLoss(kappa=30.0), clip_func=None, binary_step=1, num_iter=n_iter, **HITADV_HP)
+        torch.manual_seed(0)
+        t0 = time.time()
+        att.attack(data, target)
+        torch.cuda.synchronize()
+        return att, time.time() - t0
+
+    run(max(5, args.warmup))
+    sampler = ClockSampler(local) if rank == 0 else None
+    sharding.barrier()
+    launches0 = _lib.launch_count()
+    if sampler:
+        sampler.begin()
+    att, wall = run(steps)
+    if sampler:
+        sampler.end()
+    sharding.barrier()
+    launches = (_lib.launch_count() - launches0) // steps
+    loop_ms = sharding.max_over_ranks(att.loop_ms / steps)
+    e2e_ms = sharding.max_over_ranks(wall * 1e3 / steps)
+    clocks = sampler.stop() if sampler else {}
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+    if rank != 0:
+        return
+    line = {"metric": HITADV_METRIC, "value": world * B / (loop_ms * 1e-3), "unit": "cloud-iterations/s", "n_gpus": world,
+            "steps": steps, "warmup": max(5, args.warmup), "ms_per_step": loop_ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": name, "batch_per_gpu": B, "points": K, "attack_iters_per_s_per_batch": 1e3 / loop_ms,
+                       "note": "value = device time of the iteration loop (CUDA events); e2e = whole attack() call: host data "
+                               "in, one-off centre selection, iterations, adversarial clouds back to the host"},
+            "clocks": clocks,
+            "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": "cloud-iterations/s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": int(data.numel() * 4 / steps), "d2h_bytes_per_step": int(B * K * 3 * 8 / steps)},
+            "gpu_launches": int(launches)}
+    if world == 1 and not args.no_cpu_baseline:
+        try:  # the reference's torch program on THIS GPU (the second bar of BASELINE.md section 4)
+            from oracle import hitadv_port as hp
+
+            torch.manual_seed(0)
+            n_ref = 6
+            torch.cuda.synchronize()
+            t0 = time.time()
+            hp.attack(model, data.to(dev), target.to(dev), dict(HITADV_HP, kappa=30.0, binary_step=1, num_iter=n_ref))
+            torch.cuda.synchronize()
+            t_all = time.time() - t0
+            t0 = time.time()
+            hp.attack(model, data.to(dev), target.to(dev), dict(HITADV_HP, kappa=30.0, binary_step=1, num_iter=2 * n_ref))
+            torch.cuda.synchronize()
+            per_iter = (time.time() - t0 - t_all) / n_ref  # difference of two runs removes the one-off setup
+            line["reference_torch_path_on_this_gpu"] = {"value": B / per_iter, "unit": "cloud-iterations/s",
+                                                        "ms_per_step": per_iter * 1e3,
+                                                        "what": "oracle/hitadv_port.py (the reference's tensor program) on cuda:0, batch %d" % B}
+        except Exception as e:
+            line["reference_torch_path_on_this_gpu"] = {"value": None, "what": f"failed: {e}"}
+        try:
+            r = hitadv_cpu(8, K, 5)
+            line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        except Exception as e:
+            line["cpu_baseline"] = {"value": None, "unit": "cloud-iterations/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
+    print(json.dumps(line), flush=True)
+
+
 if __name__ == "__main__":
     a = parse()
-    if a.impl == "reference":
+    if a.workload == "hitadv":
+        main_hitadv(a)
+    elif a.impl == "reference":
         main_reference(a)
     else:
         main_hitgeom(a)

@@ -68,57 +68,78 @@ __global__ void __launch_bounds__(kDefThreads) deform_fwd_kernel(const float *__
   deno[(size_t)b * K + n] = den;
 }
 
-// one CTA per (b, j); threads stride over n; four block reductions (dp0, dp1, dp2, ddelta)
+// one CTA per (b, group of kJT centres); threads stride over n and share the per-point loads across the group;
+// 4*kJT block reductions (dp0, dp1, dp2, ddelta per centre) with a fixed-order tree
+constexpr int kJT = 8;
 __global__ void __launch_bounds__(kDefThreads) deform_bwd_kernel(
     const float *__restrict__ ori, const float *__restrict__ centers, const float *__restrict__ perturb,
     const float *__restrict__ delta, const float *__restrict__ out, const float *__restrict__ deno,
     const float *__restrict__ grad_out, int K, int J, float *__restrict__ grad_perturb,
     float *__restrict__ grad_delta) {
-  const int b = blockIdx.y, j = blockIdx.x, tid = threadIdx.x;
-  const float c0 = centers[((size_t)b * 3 + 0) * J + j], c1 = centers[((size_t)b * 3 + 1) * J + j],
-              c2 = centers[((size_t)b * 3 + 2) * J + j];
-  const float p0 = perturb[((size_t)b * J + j) * 3 + 0], p1 = perturb[((size_t)b * J + j) * 3 + 1],
-              p2 = perturb[((size_t)b * J + j) * 3 + 2];
-  const float d = delta[(size_t)b * J + j];
-  const float inv2d2 = 1.0f / (2.0f * d * d), invd3 = 1.0f / (d * d * d);
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, sd = 0.f;
+  const int b = blockIdx.y, j0 = blockIdx.x * kJT, tid = threadIdx.x;
+  float c0[kJT], c1[kJT], c2[kJT], p0[kJT], p1[kJT], p2[kJT], inv2d2[kJT], invd3[kJT];
+  float s0[kJT], s1[kJT], s2[kJT], sd[kJT];
+#pragma unroll
+  for (int u = 0; u < kJT; ++u) {
+    const int j = min(j0 + u, J - 1);
+    c0[u] = centers[((size_t)b * 3 + 0) * J + j];
+    c1[u] = centers[((size_t)b * 3 + 1) * J + j];
+    c2[u] = centers[((size_t)b * 3 + 2) * J + j];
+    p0[u] = perturb[((size_t)b * J + j) * 3 + 0];
+    p1[u] = perturb[((size_t)b * J + j) * 3 + 1];
+    p2[u] = perturb[((size_t)b * J + j) * 3 + 2];
+    const float d = delta[(size_t)b * J + j];
+    inv2d2[u] = 1.0f / (2.0f * d * d);
+    invd3[u] = 1.0f / (d * d * d);
+    s0[u] = s1[u] = s2[u] = sd[u] = 0.f;
+  }
   for (int n = tid; n < K; n += kDefThreads) {
     const float x0 = ori[((size_t)b * 3 + 0) * K + n], x1 = ori[((size_t)b * 3 + 1) * K + n],
                 x2 = ori[((size_t)b * 3 + 2) * K + n];
-    float r;
-    const float w = deform_weight(x0, x1, x2, c0, c1, c2, inv2d2, &r);
     const float iw = 1.0f / deno[(size_t)b * K + n];
     const float g0 = grad_out[((size_t)b * 3 + 0) * K + n], g1 = grad_out[((size_t)b * 3 + 1) * K + n],
                 g2 = grad_out[((size_t)b * 3 + 2) * K + n];
-    const float wn = w * iw;
-    s0 += g0 * wn;
-    s1 += g1 * wn;
-    s2 += g2 * wn;
     const float o0 = out[((size_t)b * 3 + 0) * K + n], o1 = out[((size_t)b * 3 + 1) * K + n],
                 o2 = out[((size_t)b * 3 + 2) * K + n];
-    const float dw = (g0 * ((x0 + p0) - o0) + g1 * ((x1 + p1) - o1) + g2 * ((x2 + p2) - o2)) * iw;
-    sd += dw * w * r * invd3;
-  }
-  __shared__ float red[4][kDefThreads];
-  red[0][tid] = s0;
-  red[1][tid] = s1;
-  red[2][tid] = s2;
-  red[3][tid] = sd;
-  __syncthreads();
-  for (int st = kDefThreads / 2; st > 0; st >>= 1) {
-    if (tid < st) {
-      red[0][tid] += red[0][tid + st];
-      red[1][tid] += red[1][tid + st];
-      red[2][tid] += red[2][tid + st];
-      red[3][tid] += red[3][tid + st];
+    const float gx = g0 * (x0 - o0) + g1 * (x1 - o1) + g2 * (x2 - o2);
+#pragma unroll
+    for (int u = 0; u < kJT; ++u) {
+      float r;
+      const float w = deform_weight(x0, x1, x2, c0[u], c1[u], c2[u], inv2d2[u], &r);
+      const float wn = w * iw;
+      s0[u] += g0 * wn;
+      s1[u] += g1 * wn;
+      s2[u] += g2 * wn;
+      const float dw = (gx + g0 * p0[u] + g1 * p1[u] + g2 * p2[u]) * iw;  // sum_c g_c ((x_c + p_c) - out_c) / W
+      sd[u] += dw * w * r * invd3[u];
     }
-    __syncthreads();
   }
-  if (tid == 0) {
-    grad_perturb[((size_t)b * J + j) * 3 + 0] = red[0][0];
-    grad_perturb[((size_t)b * J + j) * 3 + 1] = red[1][0];
-    grad_perturb[((size_t)b * J + j) * 3 + 2] = red[2][0];
-    grad_delta[(size_t)b * J + j] = red[3][0];
+  __shared__ float red[4 * kJT][kDefThreads + 1];
+#pragma unroll
+  for (int u = 0; u < kJT; ++u) {
+    red[4 * u + 0][tid] = s0[u];
+    red[4 * u + 1][tid] = s1[u];
+    red[4 * u + 2][tid] = s2[u];
+    red[4 * u + 3][tid] = sd[u];
+  }
+  __syncthreads();
+  // 4*kJT rows of kDefThreads partials: warp w reduces rows w, w+4, ... in a fixed order
+  const int lane = tid & 31, warp = tid >> 5;
+  for (int row = warp; row < 4 * kJT; row += kDefThreads / 32) {
+    float v = 0.f;
+#pragma unroll
+    for (int q = 0; q < kDefThreads / 32; ++q) v += red[row][lane + 32 * q];
+#pragma unroll
+    for (int st = 16; st > 0; st >>= 1) v += __shfl_down_sync(0xffffffffu, v, st);
+    if (lane == 0) {
+      const int u = row >> 2, comp = row & 3, j = j0 + u;
+      if (j < J) {
+        if (comp < 3)
+          grad_perturb[((size_t)b * J + j) * 3 + comp] = v;
+        else
+          grad_delta[(size_t)b * J + j] = v;
+      }
+    }
   }
 }
 
@@ -145,8 +166,8 @@ HG_API int hg_hitadv_deform_bwd_f32(const float *ori, const float *centers, cons
              "hitadv_deform_bwd: null pointer");
   HG_REQUIRE(B > 0 && K > 0 && J > 0, HG_E_BADARG, "hitadv_deform_bwd: sizes must be positive");
   HG_REQUIRE(B <= 65535, HG_E_UNSUPPORTED, "hitadv_deform_bwd: B too large");
-  deform_bwd_kernel<<<dim3(J, B), kDefThreads, 0, hg_stream(stream_)>>>(ori, centers, perturb, delta, out, deno,
-                                                                        grad_out, K, J, grad_perturb, grad_delta);
+  deform_bwd_kernel<<<dim3((J + kJT - 1) / kJT, B), kDefThreads, 0, hg_stream(stream_)>>>(
+      ori, centers, perturb, delta, out, deno, grad_out, K, J, grad_perturb, grad_delta);
   HG_CHECK_LAUNCH("deform_bwd_kernel");
   return HG_OK;
 }

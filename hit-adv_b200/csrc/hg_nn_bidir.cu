@@ -394,10 +394,16 @@ __global__ void __launch_bounds__(256) set_loss_bwd_kernel(
     const float *__restrict__ g_other /*[B] upstream of the loss that scatters into self*/,
     const int *__restrict__ hd_self /*[B] or null*/, const int *__restrict__ hd_other /*[B] or null*/, int B, int Ns,
     int No, int D, int mode, float *__restrict__ grad_self) {
-  const long long total = (long long)B * Ns;
+  // D == 3 (the hot case): one thread per point, looping over its 3 coordinates.  Large D (channel-first input,
+  // 3 "points" of dimension K): one thread per (point, coordinate) so that loads/stores coalesce.
+  const int cper = (D > 8) ? 1 : D;          // coordinates handled per thread
+  const int nchunk = (D + cper - 1) / cper;  // threads per point
+  const long long total = (long long)B * Ns * nchunk;
   for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total;
        g += (long long)gridDim.x * blockDim.x) {
-    const int b = (int)(g / Ns), s = (int)(g % Ns);
+    const int chunk = (int)(g % nchunk);
+    const long long pt = g / nchunk;
+    const int b = (int)(pt / Ns), s = (int)(pt % Ns);
     const float *ps = self_pts + ((size_t)b * Ns + s) * D;
     const float *po = other_pts + (size_t)b * No * D;
     float cs, co;
@@ -413,7 +419,7 @@ __global__ void __launch_bounds__(256) set_loss_bwd_kernel(
     const int *lst = rev_list + (size_t)b * No;
     const int p0 = off[s], p1 = off[s + 1];
     const int hdo = (mode == HG_MODE_CHAMFER) ? -1 : hd_other[b];
-    for (int c = 0; c < D; ++c) {
+    for (int c = chunk * cper; c < min(D, (chunk + 1) * cper); ++c) {
       const float v = ps[c];
       float acc = 0.f;
       if (cs != 0.f) acc = cs * (2.0f * (v - po[(size_t)a * D + c]));
@@ -577,7 +583,7 @@ HG_API int hg_set_loss_bwd_f32(const float *gts, const float *preds, const int *
   HgCsr rev2;
   int rc = hg_csr_build_unordered(arg2, B, N2, N1, workspace, hg_csr_workspace_bytes(B, N1, N2), &rev2, stream);
   if (rc) return rc;
-  const long long tp = (long long)B * N1;
+  const long long tp = (long long)B * N1 * (D > 8 ? D : 1);
   set_loss_bwd_kernel<<<grid_for(tp, 256), 256, 0, stream>>>(preds, gts, arg1, rev2.off, rev2.list, g1, g2, hd_arg1,
                                                              hd_arg2, B, N1, N2, D, mode, grad_preds);
   HG_CHECK_LAUNCH("set_loss_bwd_kernel(preds)");
@@ -586,7 +592,7 @@ HG_API int hg_set_loss_bwd_f32(const float *gts, const float *preds, const int *
     void *ws2 = (char *)workspace + hg_csr_workspace_bytes(B, N1, N2);
     rc = hg_csr_build_unordered(arg1, B, N1, N2, ws2, hg_csr_workspace_bytes(B, N2, N1), &rev1, stream);
     if (rc) return rc;
-    const long long tg = (long long)B * N2;
+    const long long tg = (long long)B * N2 * (D > 8 ? D : 1);
     set_loss_bwd_kernel<<<grid_for(tg, 256), 256, 0, stream>>>(gts, preds, arg2, rev1.off, rev1.list, g2, g1, hd_arg2,
                                                                hd_arg1, B, N2, N1, D, mode, grad_gts);
     HG_CHECK_LAUNCH("set_loss_bwd_kernel(gts)");

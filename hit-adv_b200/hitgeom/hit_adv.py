@@ -67,6 +67,7 @@ class HiT_ADV:
         self.alpha = alpha
         self.total_central_num = total_central_num
         self.iterations_run = 0  # inner iterations of the last attack() call (for the benchmark)
+        self.loop_ms = 0.0
 
     # ---- helpers (HiT_ADV.py:298-346) ---------------------------------------------------------------------------
     @staticmethod
@@ -186,6 +187,8 @@ class HiT_ADV:
         tmp_adv_data = ori_data
         dist_val = o_bestdist
         self.iterations_run = 0
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
 
         for _binary_step in range(self.binary_step):
             # same CPU-generator draws, in the same order, as HiT_ADV.py:130-134
@@ -228,8 +231,11 @@ class HiT_ADV:
                 upper_bound = torch.where(ok, upper_bound, torch.minimum(upper_bound, scale_const))
                 scale_const = (lower_bound + upper_bound) / 2.
 
+        ev1.record()
         with torch.no_grad():
             failed = lower_bound == 0.
             o_bestattack = torch.where(failed[:, None, None], tmp_adv_data.detach(), o_bestattack)
             success_num = (lower_bound > 0.).sum()
-        return o_bestattack.transpose(1, 2).double().cpu().numpy(), success_num.cpu()
+        out = o_bestattack.transpose(1, 2).double().cpu().numpy(), success_num.cpu()
+        self.loop_ms = ev0.elapsed_time(ev1)  # device time of the iteration loops of this call (benchmark)
+        return out
