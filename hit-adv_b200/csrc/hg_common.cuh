@@ -102,7 +102,8 @@ __device__ __forceinline__ float hg_warp_max_f32(float v) {
 // ---- deterministic reverse map (CSR) used by every scatter-style backward ----------------------------------
 // keys [B,E] (destination of edge e, or <0 to skip) -> off [B,N+1], list [B,E] with, for each destination,
 // its edges in ascending e.  Summing in list order is what replaces the reference's float atomicAdd.
-size_t hg_csr_workspace_bytes(int B, int N, int E);
+size_t hg_csr_workspace_bytes(int B, int N, int E);         // for hg_csr_build_unordered
+size_t hg_csr_stable_workspace_bytes(int B, int N, int E);  // for hg_csr_build
 struct HgCsr {
   int *off;   // [B, N+1]
   int *list;  // [B, E]
@@ -130,3 +131,6 @@ int hg_knn3_launch_i32(int form, const float *q, const float *r, int B, int Nq, 
                        cudaStream_t stream);
 int hg_knn3_launch_i64(int form, const float *q, const float *r, int B, int Nq, int Nr, int k1, float *vals,
                        long long *idx, cudaStream_t stream);
+size_t hg_knn3_seed_workspace_bytes(int B, int N);
+int hg_knn3_self_seeded_i32(const float *pc, int B, int N, int k1, float *vals, int *idx, void *workspace,
+                            size_t workspace_bytes, cudaStream_t stream);

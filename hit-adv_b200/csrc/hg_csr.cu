@@ -9,8 +9,12 @@
 
 namespace {
 
-constexpr int kCsrThreads = 128;
+constexpr int kCsrThreads = 256;
+constexpr int kCsrWarps = kCsrThreads / 32;
 
+// One CTA per cloud.  The edge range is cut into kCsrWarps contiguous segments, one per warp: per-warp key
+// counts -> exclusive prefix over (key, warp) -> every warp places its own segment stably (chunks of 32 edges in
+// ascending order, rank inside a chunk from __match_any_sync), all warps in parallel.
 __global__ void __launch_bounds__(kCsrThreads) csr_build_kernel(const int *__restrict__ keys, int E, int N,
                                                                 int *__restrict__ off_all,
                                                                 int *__restrict__ cursor_all,
@@ -18,16 +22,24 @@ __global__ void __launch_bounds__(kCsrThreads) csr_build_kernel(const int *__res
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int *k = keys + (size_t)b * E;
   int *off = off_all + (size_t)b * (N + 1);
-  int *cursor = cursor_all + (size_t)b * N;
+  int *cursor = cursor_all + (size_t)b * kCsrWarps * N;  // [kCsrWarps][N]
   int *list = list_all + (size_t)b * E;
-  __shared__ int warp_tot[kCsrThreads / 32];
+  __shared__ int warp_tot[kCsrWarps];
   __shared__ int carry_s;
 
+  const int seg = ((E + kCsrWarps - 1) / kCsrWarps + 31) / 32 * 32;  // edges per warp segment (multiple of 32)
+  const int e_lo = min(E, warp * seg), e_hi = min(E, (warp + 1) * seg);
+  int *mine = cursor + (size_t)warp * N;
+
   for (int i = tid; i <= N; i += kCsrThreads) off[i] = 0;
+  for (int i = tid; i < kCsrWarps * N; i += kCsrThreads) cursor[i] = 0;
   __syncthreads();
-  for (int e = tid; e < E; e += kCsrThreads) {
+  for (int e = e_lo + lane; e < e_hi; e += 32) {
     const int key = k[e];
-    if (key >= 0 && key < N) atomicAdd(&off[key + 1], 1);
+    if (key >= 0 && key < N) {
+      atomicAdd(&off[key + 1], 1);
+      atomicAdd(&mine[key], 1);
+    }
   }
   if (tid == 0) carry_s = 0;
   __syncthreads();
@@ -49,25 +61,30 @@ __global__ void __launch_bounds__(kCsrThreads) csr_build_kernel(const int *__res
     if (tid == kCsrThreads - 1) carry_s = v + add;
     __syncthreads();
   }
-  for (int i = tid; i < N; i += kCsrThreads) cursor[i] = off[i];
-  __syncthreads();
-  // stable placement by one warp: chunks of 32 edges in ascending order, rank inside the chunk by lane
-  if (warp == 0) {
-    for (int base = 0; base < E; base += 32) {
-      const int e = base + lane;
-      int key = (e < E) ? k[e] : -1;
-      if (key >= N) key = -1;
-      const unsigned same = __match_any_sync(0xffffffffu, key);
-      const int rank = __popc(same & ((1u << lane) - 1u));
-      int pos = 0;
-      if (key >= 0) pos = cursor[key] + rank;
-      __syncwarp();
-      if (key >= 0) {
-        list[pos] = e;
-        if (rank == 0) cursor[key] = pos + __popc(same);
-      }
-      __syncwarp();
+  // per-warp start of every key: segment start + edges of that key in the earlier warps' segments
+  for (int key = tid; key < N; key += kCsrThreads) {
+    int run = off[key];
+    for (int w = 0; w < kCsrWarps; ++w) {
+      const int c = cursor[(size_t)w * N + key];
+      cursor[(size_t)w * N + key] = run;
+      run += c;
     }
+  }
+  __syncthreads();
+  for (int base = e_lo; base < e_hi; base += 32) {
+    const int e = base + lane;
+    int key = (e < e_hi) ? k[e] : -1;
+    if (key >= N) key = -1;
+    const unsigned same = __match_any_sync(0xffffffffu, key);
+    const int rank = __popc(same & ((1u << lane) - 1u));
+    int pos = 0;
+    if (key >= 0) pos = mine[key] + rank;
+    __syncwarp();
+    if (key >= 0) {
+      list[pos] = e;
+      if (rank == 0) mine[key] = pos + __popc(same);
+    }
+    __syncwarp();
   }
 }
 
@@ -78,15 +95,20 @@ size_t hg_csr_workspace_bytes(int B, int N, int E) {
          hg_align((size_t)B * E * sizeof(int));
 }
 
+size_t hg_csr_stable_workspace_bytes(int B, int N, int E) {
+  return hg_align((size_t)B * (N + 1) * sizeof(int)) + hg_align((size_t)B * kCsrWarps * N * sizeof(int)) +
+         hg_align((size_t)B * E * sizeof(int));
+}
+
 int hg_csr_build(const int *keys, int B, int E, int N, void *workspace, size_t workspace_bytes, HgCsr *out,
                  cudaStream_t stream) {
-  HG_REQUIRE(workspace && workspace_bytes >= hg_csr_workspace_bytes(B, N, E), HG_E_WORKSPACE,
-             "csr: workspace too small (%zu < %zu)", workspace_bytes, hg_csr_workspace_bytes(B, N, E));
+  HG_REQUIRE(workspace && workspace_bytes >= hg_csr_stable_workspace_bytes(B, N, E), HG_E_WORKSPACE,
+             "csr: workspace too small (%zu < %zu)", workspace_bytes, hg_csr_stable_workspace_bytes(B, N, E));
   char *p = (char *)workspace;
   int *off = (int *)p;
   p += hg_align((size_t)B * (N + 1) * sizeof(int));
   int *cursor = (int *)p;
-  p += hg_align((size_t)B * N * sizeof(int));
+  p += hg_align((size_t)B * kCsrWarps * N * sizeof(int));
   int *list = (int *)p;
   csr_build_kernel<<<B, kCsrThreads, 0, stream>>>(keys, E, N, off, cursor, list);
   HG_CHECK_LAUNCH("csr_build_kernel");

@@ -245,7 +245,7 @@ constexpr size_t kGenericScratchBytes = (size_t)256 << 20;
 HG_API size_t hg_knn_self_workspace_bytes(int B, int K, int C, int k1) {
   (void)k1;
   if (B <= 0 || K <= 0 || C <= 0) return 0;
-  if (C == 3) return 256;
+  if (C == 3) return hg_knn3_seed_workspace_bytes(B, K);
   size_t per = (size_t)K * K * sizeof(float);
   size_t nb = kGenericScratchBytes / per;
   if (nb < 1) nb = 1;
@@ -260,7 +260,7 @@ HG_API int hg_knn_self_f32(const float *pc, int B, int K, int C, int k1, float *
   HG_REQUIRE(B > 0 && K > 0 && C > 0, HG_E_BADARG, "knn_self: sizes must be positive");
   HG_REQUIRE(k1 >= 1 && k1 <= 32 && k1 <= K, HG_E_BADARG, "knn_self: need 1 <= k <= min(32, K); got k=%d K=%d", k1, K);
   HG_REQUIRE(B <= 65535, HG_E_UNSUPPORTED, "knn_self: B=%d > 65535 clouds per call", B);
-  if (C == 3) return hg_knn3_launch_i32(HG_KNN_FORM_EXPANDED, pc, pc, B, K, K, k1, vals, idx, stream);
+  if (C == 3) return hg_knn3_self_seeded_i32(pc, B, K, k1, vals, idx, workspace, workspace_bytes, stream);
   const size_t need = hg_knn_self_workspace_bytes(B, K, C, k1);
   HG_REQUIRE(workspace && workspace_bytes >= need, HG_E_WORKSPACE, "knn_self: workspace too small (%zu < %zu)",
              workspace_bytes, need);

@@ -72,14 +72,15 @@ struct TopK {
 template <int FORM, int QT, int KM, typename IdxT>
 __global__ void __launch_bounds__(kThreads) knn3_kernel(const float *__restrict__ queries,
                                                         const float *__restrict__ refs, int Nq, int Nr, int k1,
-                                                        float *__restrict__ vals, IdxT *__restrict__ idx) {
+                                                        float *__restrict__ vals, IdxT *__restrict__ idx,
+                                                        const float *__restrict__ thr0 /*[B,Nq] or null*/) {
   __shared__ float4 cand[kTileC];  // two float4 per candidate pair
   const int b = blockIdx.y, tid = threadIdx.x;
   const float *q = queries + (size_t)b * Nq * 3;
   const float *r = refs + (size_t)b * Nr * 3;
 
   constexpr int MW = kTileC / 64;  // hit-mask words per query: one bit per candidate pair of a tile
-  float a0[QT], a1[QT], a2[QT], a3[QT], thr[QT];
+  float a0[QT], a1[QT], a2[QT], a3[QT], thr[QT], seed[QT];
   unsigned mask[QT][MW];
   TopK<KM> top[QT];
 #pragma unroll
@@ -102,7 +103,10 @@ __global__ void __launch_bounds__(kThreads) knn3_kernel(const float *__restrict_
       a2[t] = q2;
       a3[t] = 0.f;
     }
-    thr[t] = CUDART_INF_F;
+    // optional upper bound on this query's KM-th distance (knn_seed_kernel): the filter starts tight instead of
+    // at +inf, so only ~KM candidates ever reach the drain instead of ~KM ln(N/KM)
+    seed[t] = (thr0 != nullptr && i < Nq) ? thr0[(size_t)b * Nq + i] : CUDART_INF_F;
+    thr[t] = seed[t];
 #pragma unroll
     for (int w = 0; w < MW; ++w) mask[t][w] = 0u;
     top[t].init();
@@ -194,7 +198,7 @@ __global__ void __launch_bounds__(kThreads) knn3_kernel(const float *__restrict_
           top[t].push(knn_dist_exact<FORM>(a0[t], a1[t], a2[t], a3[t], cA.x, cA.z, cB.x, cB.z), j0);
           top[t].push(knn_dist_exact<FORM>(a0[t], a1[t], a2[t], a3[t], cA.y, cA.w, cB.y, cB.w), j0 + 1);
         }
-        thr[t] = top[t].v[KM - 1];
+        thr[t] = fminf(seed[t], top[t].v[KM - 1]);
       }
       p0 += cnt;
       if (base == 0 && step < 32 && p0 >= 2 * step) step *= 2;  // 4,4,8,16,32,32,...
@@ -218,10 +222,10 @@ __global__ void __launch_bounds__(kThreads) knn3_kernel(const float *__restrict_
 
 template <int FORM, int QT, int KM, typename IdxT>
 int launch_qt(const float *q, const float *r, int B, int Nq, int Nr, int k1, float *vals, IdxT *idx,
-              cudaStream_t stream) {
+              const float *thr0, cudaStream_t stream) {
   dim3 grid((Nq + QT * kThreads - 1) / (QT * kThreads), B);
   const bool prof = hg_prof_begin(HG_PROF_KNN, stream);
-  knn3_kernel<FORM, QT, KM, IdxT><<<grid, kThreads, 0, stream>>>(q, r, Nq, Nr, k1, vals, idx);
+  knn3_kernel<FORM, QT, KM, IdxT><<<grid, kThreads, 0, stream>>>(q, r, Nq, Nr, k1, vals, idx, thr0);
   hg_prof_end(HG_PROF_KNN, stream, prof);
   HG_CHECK_LAUNCH("knn3_kernel");
   return HG_OK;
@@ -229,7 +233,7 @@ int launch_qt(const float *q, const float *r, int B, int Nq, int Nr, int k1, flo
 
 template <int FORM, typename IdxT>
 int launch_form(const float *q, const float *r, int B, int Nq, int Nr, int k1, float *vals, IdxT *idx,
-                cudaStream_t stream) {
+                const float *thr0, cudaStream_t stream) {
   if (k1 < 1 || k1 > 32) {
     hg_set_error("knn: k=%d outside [1,32]", k1);
     return HG_E_UNSUPPORTED;
@@ -237,15 +241,142 @@ int launch_form(const float *q, const float *r, int B, int Nq, int Nr, int k1, f
   // queries per lane: amortise the candidate loads, but keep small query sets spread over the machine and the
   // register-resident lists (2*KM registers per query) within budget
   if (k1 <= 6) {
-    if (Nq >= 3 * kThreads) return launch_qt<FORM, 4, 6, IdxT>(q, r, B, Nq, Nr, k1, vals, idx, stream);
-    if (Nq > kThreads) return launch_qt<FORM, 2, 6, IdxT>(q, r, B, Nq, Nr, k1, vals, idx, stream);
-    return launch_qt<FORM, 1, 6, IdxT>(q, r, B, Nq, Nr, k1, vals, idx, stream);
+    if (Nq >= 3 * kThreads) return launch_qt<FORM, 4, 6, IdxT>(q, r, B, Nq, Nr, k1, vals, idx, thr0, stream);
+    if (Nq > kThreads) return launch_qt<FORM, 2, 6, IdxT>(q, r, B, Nq, Nr, k1, vals, idx, thr0, stream);
+    return launch_qt<FORM, 1, 6, IdxT>(q, r, B, Nq, Nr, k1, vals, idx, thr0, stream);
   }
   if (k1 <= 20) {
-    if (Nq > kThreads) return launch_qt<FORM, 2, 20, IdxT>(q, r, B, Nq, Nr, k1, vals, idx, stream);
-    return launch_qt<FORM, 1, 20, IdxT>(q, r, B, Nq, Nr, k1, vals, idx, stream);
+    if (Nq > kThreads) return launch_qt<FORM, 2, 20, IdxT>(q, r, B, Nq, Nr, k1, vals, idx, thr0, stream);
+    return launch_qt<FORM, 1, 20, IdxT>(q, r, B, Nq, Nr, k1, vals, idx, thr0, stream);
   }
-  return launch_qt<FORM, 1, 32, IdxT>(q, r, B, Nq, Nr, k1, vals, idx, stream);
+  return launch_qt<FORM, 1, 32, IdxT>(q, r, B, Nq, Nr, k1, vals, idx, thr0, stream);
+}
+
+// ---- threshold seeding for self-kNN ---------------------------------------------------------------------------
+// A uniform grid over the cloud's bounding box (about 3 points per cell) gives every query an exact UPPER BOUND on its
+// KM-th smallest distance: the KM-th smallest over the points of its 27 neighbouring cells, evaluated with the same
+// expanded-form arithmetic (those points are real candidates, so the true KM-th distance cannot be larger).  The
+// brute-force pass still evaluates all N^2 pairs and still decides every index itself; the seed only spares the
+// ~KM ln(N/KM) insertions a cold threshold costs.  The bound is nudged up one ulp so that the strict '<' of the
+// filter keeps candidates EQUAL to it.
+constexpr int kMaxSeedCand = 512;
+
+__global__ void __launch_bounds__(256) knn_cells_kernel(const float *__restrict__ pc, int N, int G,
+                                                        int *__restrict__ cellid, float *__restrict__ params) {
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const float *p = pc + (size_t)b * N * 3;
+  __shared__ float red[6][256];
+  float lo[3] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F}, hi[3] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
+  for (int i = tid; i < N; i += 256)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float v = p[(size_t)i * 3 + c];
+      lo[c] = fminf(lo[c], v);
+      hi[c] = fmaxf(hi[c], v);
+    }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    red[c][tid] = lo[c];
+    red[3 + c][tid] = hi[c];
+  }
+  __syncthreads();
+  for (int st = 128; st > 0; st >>= 1) {
+    if (tid < st)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        red[c][tid] = fminf(red[c][tid], red[c][tid + st]);
+        red[3 + c][tid] = fmaxf(red[3 + c][tid], red[3 + c][tid + st]);
+      }
+    __syncthreads();
+  }
+  float mn[3], inv[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    mn[c] = red[c][0];
+    const float ext = red[3 + c][0] - mn[c];
+    inv[c] = (ext > 0.f && ext < CUDART_INF_F) ? (float)G / ext : 0.f;
+  }
+  if (tid < 3) {
+    params[b * 8 + tid] = mn[tid];
+    params[b * 8 + 3 + tid] = inv[tid];
+  }
+  for (int i = tid; i < N; i += 256) {
+    int cc[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float f = (p[(size_t)i * 3 + c] - mn[c]) * inv[c];
+      cc[c] = (f == f) ? min(max((int)f, 0), G - 1) : 0;
+    }
+    cellid[(size_t)b * N + i] = (cc[2] * G + cc[1]) * G + cc[0];
+  }
+}
+
+// points re-ordered by cell (the CSR list is a permutation of the cloud grouped by cell): (x, y, z, xx)
+__global__ void __launch_bounds__(256) knn_cell_sort_kernel(const float *__restrict__ pc, const int *__restrict__ list,
+                                                            long long total, int N, float4 *__restrict__ sorted) {
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total;
+       g += (long long)gridDim.x * blockDim.x) {
+    const long long b = g / N;
+    const float *p = pc + ((size_t)b * N + list[g]) * 3;
+    const float x = p[0], y = p[1], z = p[2];
+    sorted[g] = make_float4(x, y, z, hg_sumsq3_seq(x, y, z));
+  }
+}
+
+// one thread per query, in CELL ORDER: the 32 queries of a warp sit in a handful of neighbouring cells, so their
+// candidate runs (3 x-adjacent cells are contiguous in `sorted`) overlap and come from L1
+template <int KM>
+__global__ void __launch_bounds__(128) knn_seed_kernel(const float4 *__restrict__ sorted, int N, int G,
+                                                       const float *__restrict__ params, const int *__restrict__ off,
+                                                       const int *__restrict__ list, float *__restrict__ thr0) {
+  const int b = blockIdx.y, s_q = blockIdx.x * 128 + threadIdx.x;
+  if (s_q >= N) return;
+  const float4 *pts = sorted + (size_t)b * N;
+  const int ncell = G * G * G;
+  const int *o = off + (size_t)b * (ncell + 1);
+  const float4 q = pts[s_q];
+  const float a0 = -2.0f * q.x, a1 = -2.0f * q.y, a2 = -2.0f * q.z, a3 = q.w;
+  int cc[3];
+  const float qq[3] = {q.x, q.y, q.z};
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {  // same expression as knn_cells_kernel -> same cell
+    const float f = (qq[c] - params[b * 8 + c]) * params[b * 8 + 3 + c];
+    cc[c] = (f == f) ? min(max((int)f, 0), G - 1) : 0;
+  }
+  float v[KM];
+#pragma unroll
+  for (int t = 0; t < KM; ++t) v[t] = CUDART_INF_F;
+  int seen = 0;
+  for (int dz = -1; dz <= 1 && seen < kMaxSeedCand; ++dz)
+    for (int dy = -1; dy <= 1 && seen < kMaxSeedCand; ++dy) {
+      const int z = cc[2] + dz, y = cc[1] + dy;
+      if (z < 0 || z >= G || y < 0 || y >= G) continue;
+      const int x0 = max(cc[0] - 1, 0), x1 = min(cc[0] + 1, G - 1);
+      const int c0 = (z * G + y) * G + x0, c1 = (z * G + y) * G + x1;
+      for (int t = o[c0]; t < o[c1 + 1] && seen < kMaxSeedCand; ++t, ++seen) {
+        const float4 r = pts[t];
+        const float d = knn_dist_exact<HG_KNN_FORM_EXPANDED>(a0, a1, a2, a3, r.x, r.y, r.z, r.w);
+        if (d < v[KM - 1]) {
+          v[KM - 1] = d;
+#pragma unroll
+          for (int u = KM - 1; u > 0; --u)
+            if (v[u] < v[u - 1]) {
+              const float tv = v[u];
+              v[u] = v[u - 1];
+              v[u - 1] = tv;
+            }
+        }
+      }
+    }
+  const float bound = v[KM - 1];
+  thr0[(size_t)b * N + list[(size_t)b * N + s_q]] = (bound < CUDART_INF_F) ? nextafterf(bound, CUDART_INF_F) : CUDART_INF_F;
+}
+
+int seed_grid(int N) {
+  int G = (int)lroundf(cbrtf((float)N / 3.0f));
+  if (G < 1) G = 1;
+  if (G > 40) G = 40;
+  return G;
 }
 
 }  // namespace
@@ -253,13 +384,59 @@ int launch_form(const float *q, const float *r, int B, int Nq, int Nr, int k1, f
 int hg_knn3_launch_i32(int form, const float *q, const float *r, int B, int Nq, int Nr, int k1, float *vals, int *idx,
                        cudaStream_t stream) {
   return form == HG_KNN_FORM_EXPANDED
-             ? launch_form<HG_KNN_FORM_EXPANDED, int>(q, r, B, Nq, Nr, k1, vals, idx, stream)
-             : launch_form<HG_KNN_FORM_DIRECT, int>(q, r, B, Nq, Nr, k1, vals, idx, stream);
+             ? launch_form<HG_KNN_FORM_EXPANDED, int>(q, r, B, Nq, Nr, k1, vals, idx, nullptr, stream)
+             : launch_form<HG_KNN_FORM_DIRECT, int>(q, r, B, Nq, Nr, k1, vals, idx, nullptr, stream);
 }
 
 int hg_knn3_launch_i64(int form, const float *q, const float *r, int B, int Nq, int Nr, int k1, float *vals,
                        long long *idx, cudaStream_t stream) {
   return form == HG_KNN_FORM_EXPANDED
-             ? launch_form<HG_KNN_FORM_EXPANDED, long long>(q, r, B, Nq, Nr, k1, vals, idx, stream)
-             : launch_form<HG_KNN_FORM_DIRECT, long long>(q, r, B, Nq, Nr, k1, vals, idx, stream);
+             ? launch_form<HG_KNN_FORM_EXPANDED, long long>(q, r, B, Nq, Nr, k1, vals, idx, nullptr, stream)
+             : launch_form<HG_KNN_FORM_DIRECT, long long>(q, r, B, Nq, Nr, k1, vals, idx, nullptr, stream);
+}
+
+size_t hg_knn3_seed_workspace_bytes(int B, int N) {
+  const int G = seed_grid(N);
+  return hg_align((size_t)B * N * sizeof(int)) + hg_align((size_t)B * 8 * sizeof(float)) +
+         hg_align((size_t)B * N * sizeof(float)) + hg_align((size_t)B * N * sizeof(float4)) +
+         hg_csr_workspace_bytes(B, G * G * G, N);
+}
+
+// self-kNN (expanded form) with grid-seeded thresholds; falls back to the unseeded launch for small clouds
+int hg_knn3_self_seeded_i32(const float *pc, int B, int N, int k1, float *vals, int *idx, void *workspace,
+                            size_t workspace_bytes, cudaStream_t stream) {
+  if (N < 512 || k1 > 32 || workspace == nullptr || workspace_bytes < hg_knn3_seed_workspace_bytes(B, N))
+    return launch_form<HG_KNN_FORM_EXPANDED, int>(pc, pc, B, N, N, k1, vals, idx, nullptr, stream);
+  const int G = seed_grid(N), ncell = G * G * G;
+  char *w = (char *)workspace;
+  int *cellid = (int *)w;
+  w += hg_align((size_t)B * N * sizeof(int));
+  float *params = (float *)w;
+  w += hg_align((size_t)B * 8 * sizeof(float));
+  float *thr0 = (float *)w;
+  w += hg_align((size_t)B * N * sizeof(float));
+  float4 *sorted = (float4 *)w;
+  w += hg_align((size_t)B * N * sizeof(float4));
+  knn_cells_kernel<<<B, 256, 0, stream>>>(pc, N, G, cellid, params);
+  HG_CHECK_LAUNCH("knn_cells_kernel");
+  HgCsr csr;
+  int rc = hg_csr_build_unordered(cellid, B, N, ncell, w, hg_csr_workspace_bytes(B, ncell, N), &csr, stream);
+  if (rc) return rc;
+  {
+    const long long total = (long long)B * N;
+    long long blocks = (total + 255) / 256;
+    const long long cap = (long long)hg_sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    knn_cell_sort_kernel<<<(int)blocks, 256, 0, stream>>>(pc, csr.list, total, N, sorted);
+    HG_CHECK_LAUNCH("knn_cell_sort_kernel");
+  }
+  dim3 grid((N + 127) / 128, B);
+  if (k1 <= 6)
+    knn_seed_kernel<6><<<grid, 128, 0, stream>>>(sorted, N, G, params, csr.off, csr.list, thr0);
+  else if (k1 <= 20)
+    knn_seed_kernel<20><<<grid, 128, 0, stream>>>(sorted, N, G, params, csr.off, csr.list, thr0);
+  else
+    knn_seed_kernel<32><<<grid, 128, 0, stream>>>(sorted, N, G, params, csr.off, csr.list, thr0);
+  HG_CHECK_LAUNCH("knn_seed_kernel");
+  return launch_form<HG_KNN_FORM_EXPANDED, int>(pc, pc, B, N, N, k1, vals, idx, thr0, stream);
 }

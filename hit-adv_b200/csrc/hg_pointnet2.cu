@@ -78,7 +78,8 @@ int launch_gather(const float *points, const int *idx, int b, int c, int n, int 
   // stage the plane when it is re-used enough (E >= n) and fits; then one CTA column per plane
   const bool use_smem = (size_t)n * sizeof(float) <= 96 * 1024 && E >= n;
   int gx = (E + per_block - 1) / per_block;
-  const int gx_cap = use_smem ? 4 : 64;
+  // staged plane: one CTA per plane when there are enough planes to fill the machine (amortises the staging)
+  const int gx_cap = use_smem ? (planes >= 4LL * hg_sm_count() ? 1 : 4) : 64;
   if (gx > gx_cap) gx = gx_cap;
   const int gy = (int)(planes < 65535 ? planes : 65535);
   const size_t smem = use_smem ? (size_t)n * sizeof(float) : 0;
@@ -369,7 +370,7 @@ HG_API int hg_p2_gather_points(int b, int c, int n, int npoints, const float *po
 
 HG_API size_t hg_p2_scatter_workspace_bytes(int b, int n, int nedges) {
   if (b <= 0 || n <= 0 || nedges <= 0) return 0;
-  return hg_csr_workspace_bytes(b, n, nedges);
+  return hg_csr_stable_workspace_bytes(b, n, nedges);
 }
 
 HG_API int hg_p2_gather_points_grad(int b, int c, int n, int npoints, const float *grad_out, const int *idx,

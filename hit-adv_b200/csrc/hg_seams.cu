@@ -164,7 +164,7 @@ HG_API int hg_index_points_f32(const float *points, const int64_t *idx, int B, i
 
 HG_API size_t hg_index_points_grad_workspace_bytes(int B, int N, int M) {
   if (B <= 0 || N <= 0 || M <= 0) return 0;
-  return hg_align((size_t)B * M * sizeof(int)) + hg_csr_workspace_bytes(B, N, M);
+  return hg_align((size_t)B * M * sizeof(int)) + hg_csr_stable_workspace_bytes(B, N, M);
 }
 
 HG_API int hg_index_points_grad_f32(const float *grad_out, const int64_t *idx, int B, int N, int C, int M,
@@ -180,7 +180,7 @@ HG_API int hg_index_points_grad_f32(const float *grad_out, const int64_t *idx, i
   idx64_to_keys_kernel<<<grid_for(te, 256), 256, 0, stream>>>((const long long *)idx, te, N, keys);
   HG_CHECK_LAUNCH("idx64_to_keys");
   HgCsr csr;
-  int rc = hg_csr_build(keys, B, M, N, csr_ws, hg_csr_workspace_bytes(B, N, M), &csr, stream);
+  int rc = hg_csr_build(keys, B, M, N, csr_ws, hg_csr_stable_workspace_bytes(B, N, M), &csr, stream);
   if (rc) return rc;
   const long long total = (long long)B * N * C;
   index_points_grad_kernel<<<grid_for(total, 256), 256, 0, stream>>>(grad_out, csr.off, csr.list, B, N, C, M,

@@ -167,3 +167,45 @@ def test_ext_rejects_bad_input(ext):
         ext.gather_points(torch.zeros(1, 3, 8, device="cuda"), torch.zeros(1, 2, device="cuda", dtype=torch.int64))
     with pytest.raises(RuntimeError):
         ext.group_points(torch.zeros(1, 3, 8, device="cuda").transpose(1, 2), torch.zeros(1, 2, 2, device="cuda", dtype=torch.int32))
+
+
+def test_uniform_loss_pipeline_vs_oracle(oracle):
+    """The op sequence of the one in-repo pointnet2_ops caller, `uniform_loss` (FGM/GeoA3_args.py:258-302): for five
+    ball sizes, FPS(5% of n) -> gather -> ball_query -> group -> kNN inside every ball -> the uniformity statistic.
+    Every index tensor bit-exact against the oracle's composition; the final scalar to 1e-5."""
+    import math
+
+    from hitgeom.pointnet2_ops import pointnet2_utils as pu
+    from hitgeom.pytorch3d_ops import knn_points
+
+    B, n = 3, 1024
+    pc_np = clouds(B, n, 321, "surface")
+    pc = gpu(pc_np)
+    npoint = int(n * 0.05)
+    loss, loss_ref = 0.0, 0.0
+    for p in [0.004, 0.006, 0.008, 0.010, 0.012]:
+        p4 = p * 4
+        nsample, r = int(n * p4), math.sqrt(p4 * 1.0)
+        expect_len = math.sqrt(math.pi * p4 / nsample)
+        flipped = pc.transpose(1, 2).contiguous()
+        fps = pu.furthest_point_sample(pc, npoint)
+        new_xyz = pu.gather_operation(flipped, fps).transpose(1, 2).contiguous()
+        idx = pu.ball_query(r, nsample, pc, new_xyz)
+        grouped = pu.grouping_operation(flipped, idx).permute(0, 2, 3, 1).contiguous()  # [B,npoint,nsample,3]
+        grouped = torch.cat(torch.unbind(grouped, dim=1), dim=0)  # [B*npoint,nsample,3]
+        knn = knn_points(grouped, grouped, K=3)
+        d = torch.sqrt(torch.abs(knn.dists[:, :, 1:]) + 1e-12).mean(dim=-1)
+        loss = loss + (((d - expect_len) ** 2 / (expect_len + 1e-12)).reshape(-1).mean() * (p4 * 100) ** 2).item()
+        # oracle composition
+        ofps = oracle.p2_fps(pc_np, npoint)
+        onew = oracle.p2_gather(pc_np.transpose(0, 2, 1), ofps).transpose(0, 2, 1)
+        oidx = oracle.p2_ball_query(np.ascontiguousarray(onew), pc_np, np.float32(r), nsample)
+        ogrp = oracle.p2_group(pc_np.transpose(0, 2, 1), oidx).transpose(0, 2, 3, 1)
+        ogrp = np.concatenate([ogrp[:, s] for s in range(npoint)], axis=0)
+        od, oi = oracle.knn_points(ogrp, ogrp, 3, threads=4)
+        assert np.array_equal(fps.cpu().numpy(), ofps) and np.array_equal(idx.cpu().numpy(), oidx)
+        assert np.array_equal(grouped.cpu().numpy(), ogrp)
+        assert np.array_equal(knn.idx.cpu().numpy(), oi) and np.array_equal(knn.dists.cpu().numpy(), od)
+        dd = np.sqrt(np.abs(od[:, :, 1:].astype(np.float64)) + 1e-12).mean(-1)
+        loss_ref += ((dd - expect_len) ** 2 / (expect_len + 1e-12)).reshape(-1).mean() * (p4 * 100) ** 2
+    assert abs(loss - loss_ref) <= 1e-5 * abs(loss_ref)
