@@ -55,14 +55,30 @@ __global__ void __launch_bounds__(256) gather_channel_major_kernel(const float *
     }
     const float *tab = SMEM ? plane : src;
     if (VEC4) {
-      for (int e = (blockIdx.x * 256 + threadIdx.x) * 4; e < E; e += gridDim.x * 1024) {
+      const int step = gridDim.x * 1024;
+      int e = (blockIdx.x * 256 + threadIdx.x) * 4;
+      for (; e + 3 * step < E; e += 4 * step) {  // four index loads in flight per thread (memory-level parallelism)
+        int4 a[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) a[u] = *reinterpret_cast<const int4 *>(id + e + u * step);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          float4 v;
+          v.x = tab[a[u].x];
+          v.y = tab[a[u].y];
+          v.z = tab[a[u].z];
+          v.w = tab[a[u].w];
+          __stcs(reinterpret_cast<float4 *>(dst + e + u * step), v);  // streaming store: not re-read here
+        }
+      }
+      for (; e < E; e += step) {
         const int4 a = *reinterpret_cast<const int4 *>(id + e);
         float4 v;
         v.x = tab[a.x];
         v.y = tab[a.y];
         v.z = tab[a.z];
         v.w = tab[a.w];
-        __stcs(reinterpret_cast<float4 *>(dst + e), v);  // streaming store: the output is not re-read here
+        __stcs(reinterpret_cast<float4 *>(dst + e), v);
       }
     } else {
       for (int e = blockIdx.x * 256 + threadIdx.x; e < E; e += gridDim.x * 256) dst[e] = tab[__ldg(id + e)];
@@ -239,13 +255,13 @@ __global__ void __launch_bounds__(256) three_interpolate_kernel(int b, int c, in
 //               candidate; start index given; torch.max tie rule = lowest index.
 enum { POLICY_P2 = 0, POLICY_TORCH = 1 };
 
-constexpr int kFpsThreads = 256;
-
-template <int POLICY, int PPT, typename IdxT>
-__global__ void __launch_bounds__(kFpsThreads) fps_kernel(const float *__restrict__ dataset_all, int n, int m,
+// TH threads per cloud: 256 up to 4096 points, 1024 beyond (the register-resident cloud stays <= 16 points/thread
+// up to 16384 points; the per-round cost is PPT distance updates + one 64-bit block max)
+template <int POLICY, int PPT, int TH, typename IdxT>
+__global__ void __launch_bounds__(TH) fps_kernel(const float *__restrict__ dataset_all, int n, int m,
                                                           int log2bs, const long long *__restrict__ start,
                                                           IdxT *__restrict__ idxs_all) {
-  constexpr int W = kFpsThreads / 32;
+  constexpr int W = TH / 32;
   __shared__ unsigned long long wbest[2][W];
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float *dataset = dataset_all + (size_t)b * n * 3;
@@ -257,7 +273,7 @@ __global__ void __launch_bounds__(kFpsThreads) fps_kernel(const float *__restric
   unsigned low[PPT];  // ~tie-composite; 0 marks a point that can never be selected
 #pragma unroll
   for (int r = 0; r < PPT; ++r) {
-    const int k = tid + r * kFpsThreads;
+    const int k = tid + r * TH;
     px[r] = py[r] = pz[r] = 0.f;
     td[r] = 1e10f;
     low[r] = 0u;
@@ -337,24 +353,27 @@ int launch_fps(const float *dataset, int b, int n, int m, const long long *start
     const int bs = ref_opt_n_threads(n);
     while ((1 << log2bs) < bs) ++log2bs;
   }
-  const int ppt = (n + kFpsThreads - 1) / kFpsThreads;
-#define HG_FPS_CASE(P)                                                                                    \
-  if (ppt <= P) {                                                                                         \
+  const int th = n > 4096 ? 1024 : 256;
+  const int ppt = (n + th - 1) / th;
+#define HG_FPS_CASE(P, TH)                                                                                \
+  if (th == TH && ppt <= P) {                                                                             \
     const bool prof = hg_prof_begin(HG_PROF_FPS, stream);                                                 \
-    fps_kernel<POLICY, P, IdxT><<<b, kFpsThreads, 0, stream>>>(dataset, n, m, log2bs, start, idxs);      \
+    fps_kernel<POLICY, P, TH, IdxT><<<b, TH, 0, stream>>>(dataset, n, m, log2bs, start, idxs);            \
     hg_prof_end(HG_PROF_FPS, stream, prof);                                                               \
     HG_CHECK_LAUNCH("fps_kernel");                                                                        \
     return HG_OK;                                                                                         \
   }
-  HG_FPS_CASE(1)
-  HG_FPS_CASE(2)
-  HG_FPS_CASE(4)
-  HG_FPS_CASE(8)
-  HG_FPS_CASE(16)
-  HG_FPS_CASE(32)
-  HG_FPS_CASE(64)
+  HG_FPS_CASE(1, 256)
+  HG_FPS_CASE(2, 256)
+  HG_FPS_CASE(4, 256)
+  HG_FPS_CASE(8, 256)
+  HG_FPS_CASE(16, 256)
+  HG_FPS_CASE(8, 1024)
+  HG_FPS_CASE(16, 1024)
+  HG_FPS_CASE(32, 1024)
+  HG_FPS_CASE(64, 1024)
 #undef HG_FPS_CASE
-  hg_set_error("fps: n=%d > %d points per cloud unsupported", n, 64 * kFpsThreads);
+  hg_set_error("fps: n=%d > 65536 points per cloud unsupported", n);
   return HG_E_UNSUPPORTED;
 }
 

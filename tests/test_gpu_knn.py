@@ -106,3 +106,26 @@ def test_knn_points_vs_oracle(oracle, N, M, K):
     gathered = knn_gather(gpu(p2), out.idx).cpu().numpy()
     assert np.array_equal(gathered, p2[np.arange(2)[:, None, None], oi])
     assert np.array_equal(out.knn.cpu().numpy(), gathered)
+
+
+def test_config4_dgcnn_knn_full_size(oracle):
+    """BASELINE config 4 shape: DGCNN first edge-conv kNN graph, batch 32 x 1024 points, k = 20 (self included)."""
+    from hitgeom.model_seams import knn
+
+    pts = jitter(clouds(32, 1024, 4040, "surface"), 5)
+    idx = knn(gpu(pts.transpose(0, 2, 1)), 20)
+    _, oi = oracle.knn_self(pts, 20, threads=oracle.host_threads())
+    assert np.array_equal(idx.cpu().numpy(), oi)
+
+
+def test_knn_seeded_and_unseeded_agree(oracle, F):
+    """The grid-seeded thresholds (N >= 512) must not change any value or index: degenerate clouds included."""
+    for kind, n in (("surface", 4096), ("gauss", 600), ("gauss", 511)):
+        pc = clouds(2, n, 7 + n, kind)
+        pc[1, : n // 2] = pc[1, n // 2 : n // 2 * 2]  # half of cloud 1 duplicated: crowded cells, exact ties
+        vals, idx = F.knn_self(gpu(pc), 6)
+        ov, oi = oracle.knn_self(pc, 6, threads=4)
+        assert np.array_equal(vals.cpu().numpy(), ov) and np.array_equal(idx.cpu().numpy(), oi), (kind, n)
+    flat = np.zeros((1, 2048, 3), np.float32)  # every point identical: one cell, all distances equal
+    vals, idx = F.knn_self(gpu(flat), 6)
+    assert np.array_equal(idx.cpu().numpy()[0], np.tile(np.arange(6, dtype=np.int32), (2048, 1)))

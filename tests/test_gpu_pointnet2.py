@@ -209,3 +209,14 @@ def test_uniform_loss_pipeline_vs_oracle(oracle):
         dd = np.sqrt(np.abs(od[:, :, 1:].astype(np.float64)) + 1e-12).mean(-1)
         loss_ref += ((dd - expect_len) ** 2 / (expect_len + 1e-12)).reshape(-1).mean() * (p4 * 100) ** 2
     assert abs(loss - loss_ref) <= 1e-5 * abs(loss_ref)
+
+
+def test_fps_large_cloud(oracle, ext, ref_ext):
+    """16384-point clouds (config 5 size): the 1024-thread variant of the FPS kernel."""
+    xyz = clouds(2, 16384, 1616, "surface")
+    out = ext.furthest_point_sampling(gpu(xyz), 96)
+    assert np.array_equal(out.cpu().numpy(), oracle.p2_fps(xyz, 96))
+    if ref_ext is not None:
+        assert torch.equal(out, ref_ext.furthest_point_sampling(gpu(xyz), 96))
+    xyz5 = clouds(1, 5000, 55, "gauss")
+    assert np.array_equal(ext.furthest_point_sampling(gpu(xyz5), 40).cpu().numpy(), oracle.p2_fps(xyz5, 40))

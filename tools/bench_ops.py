@@ -28,10 +28,12 @@ def load_ref():
 
 
 def timeit(fn, iters=20, flush=None):
-    for _ in range(3):
+    """Mean device time of fn: all iterations enqueued back to back (the GPU stays at its load clocks), one event
+    pair per iteration on the launching stream, a single synchronize at the end; optional L2 flush between."""
+    for _ in range(5):
         fn()
     torch.cuda.synchronize()
-    tot = 0.0
+    evs = []
     for _ in range(iters):
         if flush is not None:
             flush.zero_()
@@ -39,9 +41,9 @@ def timeit(fn, iters=20, flush=None):
         a.record()
         fn()
         b.record()
-        torch.cuda.synchronize()
-        tot += a.elapsed_time(b)
-    return tot / iters
+        evs.append((a, b))
+    torch.cuda.synchronize()
+    return sum(a.elapsed_time(b) for a, b in evs) / iters
 
 
 def main():

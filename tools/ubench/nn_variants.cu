@@ -237,6 +237,81 @@ void runx4(const char *name, const float4 *xs, const float *y, float *out, uint4
          pairs / ms / 1e9, pairs * 8 / ms / 1e9 / 74.45 * 100, cudaGetErrorString(cudaGetLastError()));
 }
 
+// rows packed, STAGE-MAJOR source order (all FMUL2, then all FFMA2 #1, ...): consecutive packed instructions share
+// the row-pair operand, which the operand-reuse cache can hold -- if ptxas keeps the order
+template <int T, int WPS, int ROWS4>
+__global__ void __launch_bounds__(128, WPS) ks(const float4 *__restrict__ xs_g, const float *__restrict__ yg, float *out,
+                                               uint4 *rowout, int RB, int reps) {
+  extern __shared__ float4 xs[];
+  for (int r = threadIdx.x; r < RB + 4; r += 128) xs[r] = xs_g[(blockIdx.x * 7 + r) % 4096];
+  float y0[T], y1[T], y2[T], ry[T];
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    const float *p = yg + ((blockIdx.x * 128 + threadIdx.x) % 4096) * 64 + t * 4;
+    y0[t] = p[0]; y1[t] = p[1]; y2[t] = p[2]; ry[t] = p[3];
+  }
+  __syncthreads();
+  float cm[T];
+#pragma unroll
+  for (int t = 0; t < T; ++t) cm[t] = CUDART_INF_F;
+  const int lane = threadIdx.x & 31;
+  for (int rep = 0; rep < reps; ++rep) {
+    float4 xA = xs[0], xB = xs[1];
+    for (int r = 0; r < RB; r += 2) {
+      const float4 nA = xs[r + 2], nB = xs[r + 3];
+      const float2 X0 = make_float2(xA.x, xA.y), X1 = make_float2(xA.z, xA.w), X2 = make_float2(xB.x, xB.y), RX = make_float2(xB.z, xB.w);
+      float2 P[T], S[T];
+#pragma unroll
+      for (int t = 0; t < T; ++t) P[t] = __fmul2_rn(make_float2(y0[t], y0[t]), X0);
+#pragma unroll
+      for (int t = 0; t < T; ++t) P[t] = __ffma2_rn(make_float2(y1[t], y1[t]), X1, P[t]);
+#pragma unroll
+      for (int t = 0; t < T; ++t) P[t] = __ffma2_rn(make_float2(y2[t], y2[t]), X2, P[t]);
+#pragma unroll
+      for (int t = 0; t < T; ++t) S[t] = __fadd2_rn(RX, make_float2(ry[t], ry[t]));
+#pragma unroll
+      for (int t = 0; t < T; ++t) P[t] = __fadd2_rn(S[t], P[t]);
+#pragma unroll
+      for (int t = 0; t < T; ++t) cm[t] = fminf(fminf(cm[t], P[t].x), P[t].y);
+      float ma = fminf(P[0].x, P[1].x), mb = fminf(P[0].y, P[1].y);
+#pragma unroll
+      for (int t = 2; t < T; t += 2) {
+        ma = fminf(fminf(ma, P[t].x), P[t + 1].x);
+        mb = fminf(fminf(mb, P[t].y), P[t + 1].y);
+      }
+      const float wa = wmin(ma), wb = wmin(mb);
+      const unsigned ka = __ballot_sync(0xffffffffu, ma == wa), kb = __ballot_sync(0xffffffffu, mb == wb);
+      if (lane == 0) rowout[(blockIdx.x * 4 + (threadIdx.x >> 5)) * 64 + ((r >> 1) & 63)] = make_uint4(__float_as_uint(wa), ka, __float_as_uint(wb), kb);
+      xA = nA;
+      xB = nB;
+    }
+  }
+  float s = CUDART_INF_F;
+#pragma unroll
+  for (int t = 0; t < T; ++t) s = fminf(s, cm[t]);
+  out[blockIdx.x * 128 + threadIdx.x] = s;
+}
+
+template <int T, int WPS>
+void runs(const char *name, const float4 *xs, const float *y, float *out, uint4 *rowout) {
+  const int RB = 256, reps = 8, grid = 148 * 16;
+  const size_t smem = (RB + 4) * sizeof(float4);
+  ks<T, WPS, 0><<<grid, 128, smem>>>(xs, y, out, rowout, RB, reps);
+  cudaEvent_t a, b;
+  cudaEventCreate(&a);
+  cudaEventCreate(&b);
+  cudaEventRecord(a);
+  for (int i = 0; i < 5; ++i) ks<T, WPS, 0><<<grid, 128, smem>>>(xs, y, out, rowout, RB, reps);
+  cudaEventRecord(b);
+  cudaEventSynchronize(b);
+  float ms;
+  cudaEventElapsedTime(&ms, a, b);
+  ms /= 5;
+  const double pairs = (double)grid * 128 * T * RB * reps;
+  printf("%-44s T=%2d  %8.3f ms  %6.2fe12 pairs/s  (8 FLOP/pair: %5.1f%% of 74.45 TF)  err=%s\n", name, T, ms,
+         pairs / ms / 1e9, pairs * 8 / ms / 1e9 / 74.45 * 100, cudaGetErrorString(cudaGetLastError()));
+}
+
 template <int T, int WPS>
 void runx(const char *name, const float4 *xs, const float *y, float *out, uint4 *rowout) {
   const int RB = 256, reps = 8, grid = 148 * 16;
@@ -300,6 +375,9 @@ int main() {
   run<8, 6, 5>("full hybrid-6, T=8", xs, y, out, rowout);
   runx<16, 3>("full, rows packed (a,b), y scalar, T=16", xs, y, out, rowout);
   runx<16, 4>("full, rows packed, T=16, 4 warps/sched", xs, y, out, rowout);
+  runs<16, 3>("full, rows packed, STAGE-MAJOR, T=16 3 w/s", xs, y, out, rowout);
+  runs<16, 4>("full, rows packed, STAGE-MAJOR, T=16 4 w/s", xs, y, out, rowout);
+  runs<8, 5>("full, rows packed, STAGE-MAJOR, T=8 5 w/s", xs, y, out, rowout);
   runx<8, 5>("full, rows packed, T=8", xs, y, out, rowout);
   runx4<16, 2>("full, rows packed x4 rows, T=16, 2 w/s", xs, y, out, rowout);
   runx4<16, 3>("full, rows packed x4 rows, T=16, 3 w/s", xs, y, out, rowout);
