@@ -90,8 +90,13 @@ __global__ void __launch_bounds__(kCsrThreads) csr_build_kernel(const int *__res
 
 }  // namespace
 
+// Small problems (few edges per cloud) are launch-bound: one stable single-kernel build beats memset + count + scan
+// + fill.  hg_csr_build_unordered switches on this and the workspace formula follows it.
+static inline bool csr_small(int E) { return E <= 16384; }
+
 size_t hg_csr_workspace_bytes(int B, int N, int E) {
-  return hg_align((size_t)B * (N + 1) * sizeof(int)) + hg_align((size_t)B * N * sizeof(int)) +
+  const size_t cursors = csr_small(E) ? (size_t)kCsrWarps * N : (size_t)N;
+  return hg_align((size_t)B * (N + 1) * sizeof(int)) + hg_align((size_t)B * cursors * sizeof(int)) +
          hg_align((size_t)B * E * sizeof(int));
 }
 
@@ -184,6 +189,7 @@ int hg_csr_build_unordered(const int *keys, int B, int E, int N, void *workspace
                            cudaStream_t stream) {
   HG_REQUIRE(workspace && workspace_bytes >= hg_csr_workspace_bytes(B, N, E), HG_E_WORKSPACE,
              "csr: workspace too small (%zu < %zu)", workspace_bytes, hg_csr_workspace_bytes(B, N, E));
+  if (csr_small(E)) return hg_csr_build(keys, B, E, N, workspace, workspace_bytes, out, stream);  // sorted is fine too
   char *p = (char *)workspace;
   int *off = (int *)p;
   p += hg_align((size_t)B * (N + 1) * sizeof(int));
