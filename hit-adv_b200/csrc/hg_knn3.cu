@@ -3,14 +3,17 @@
 // Per (query, candidate) pair the FMA pipe does the same 5 operations as the Chamfer kernel (FMUL, 2 FFMA,
 // 2 FADD, issued packed as FMUL2/FFMA2/FADD2 over two CANDIDATES at a time); what differs is the selection.
 // A sorted-insertion test per pair would make every warp take the slow path on almost every candidate
-// (32 lanes x QT queries, each inserting ~k ln(N/k) times), so selection is split in two:
-//   * main loop (uniform, no divergence): for each query and candidate pair, gm = min(d, d') and ONE
-//     comparison against that query's threshold (its current k-th value); a hit only sets a bit in a
-//     per-query 32-bit mask;
-//   * drain (divergent, rare): after each sub-tile every lane walks its hit bits, re-evaluates the two
-//     candidates with the same arithmetic and inserts into its sorted list, then refreshes the thresholds.
-// The first sub-tiles are short (8, 8, 16, 32, 64 ... candidates) so that the thresholds tighten
-// geometrically and the number of stale hits stays ~k per doubling.
+// (32 lanes x QT queries, each inserting ~k ln(N/k) times), and even a compare per pair costs issue slots the
+// FMA pipe cannot hide on this part (FMNMX + FSETP + SEL ~ 5 slots next to 10.5 for the arithmetic, see
+// profiles/r01_ubench_instruction_costs.txt).  So selection is split in two:
+//   * main loop (uniform, no divergence): the threshold is folded into the last addition (filter_addend), so
+//     the SIGN BIT of the result says "below this query's threshold"; the sign bits of a group of GP candidate
+//     pairs are OR-ed (one LOP3 per pair) and shifted into a per-query 32-bit mask (one SHF per group);
+//   * drain (divergent, rare): after each window every lane walks its flagged groups, re-evaluates the group to
+//     find which candidates are below the threshold, evaluates those exactly (knn_dist_exact) and inserts them
+//     into its sorted list, then refreshes the thresholds.
+// With cold thresholds (no seed) the first windows are short (1, 1, 2, 4, 8 ... groups) so that the thresholds
+// tighten geometrically and the number of stale hits stays ~k per doubling.
 // Lists live in registers (statically indexed; KM = 6 / 20 / 32 entries, the first k are written out).
 //
 // Order of visits per query is ascending candidate index (sub-tiles ascending, bits ascending), insertion is
@@ -20,7 +23,6 @@
 namespace {
 
 constexpr int kThreads = 128;
-constexpr int kTileC = 256;  // candidates per shared-memory tile (128 pairs)
 
 // exact scalar distance, identical operation sequence to the packed main loop
 template <int FORM>
@@ -32,6 +34,37 @@ __device__ __forceinline__ float knn_dist_exact(float a0, float a1, float a2, fl
   } else {  // a = (q0,q1,q2,-), c = NEGATED candidate: d = fma(dz,dz, fma(dy,dy, dx*dx)), dx = q0 + (-c0)
     const float dx = __fadd_rn(a0, c0), dy = __fadd_rn(a1, c1), dz = __fadd_rn(a2, c2);
     return __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+  }
+}
+
+// The main loop never needs the distance itself, only whether it is below the query's threshold -- and that test
+// can be folded into the last addition.  EXPANDED: d = fl(s + a3) with s = fl(cw + nzz); with the addend
+// af = rd(a3 - thr) the sign bit of fl(s + af) is set iff s < ru(thr - a3) (a sum of two floats never rounds to
+// zero, and an exactly-zero sum is +0), and s >= ru(thr - a3) >= thr - a3 implies fl(s + a3) >= thr by
+// monotonicity of rounding: no candidate below the threshold is missed; the few extra flags (within one ulp of
+// the threshold) are rejected by the exact re-evaluation in the drain.  DIRECT: fl(d - thr) < 0 iff d < thr.
+// A +inf threshold gives af = -inf: every finite candidate is flagged; padding (s = +inf) gives NaN, sign clear.
+template <int FORM>
+__device__ __forceinline__ float filter_addend(float a3, float thr) {
+  return FORM == HG_KNN_FORM_EXPANDED ? __fsub_rd(a3, thr) : -thr;
+}
+
+// packed filter value of one candidate pair (A = (c0_j, c0_j1, c1_j, c1_j1), B = (c2_j, c2_j1, w_j, w_j1)): same
+// operation sequence as knn_dist_exact except that the last addend carries the threshold
+template <int FORM>
+__device__ __forceinline__ float2 filter_value(float a0, float a1, float a2, float af, float4 cA, float4 cB) {
+  if (FORM == HG_KNN_FORM_EXPANDED) {
+    float2 tt = __fmul2_rn(make_float2(a0, a0), make_float2(cA.x, cA.y));
+    tt = __ffma2_rn(make_float2(a1, a1), make_float2(cA.z, cA.w), tt);
+    tt = __ffma2_rn(make_float2(a2, a2), make_float2(cB.x, cB.y), tt);
+    const float2 s = __fadd2_rn(make_float2(cB.z, cB.w), tt);
+    return __fadd2_rn(s, make_float2(af, af));
+  } else {
+    const float2 dx = __fadd2_rn(make_float2(a0, a0), make_float2(cA.x, cA.y));
+    const float2 dy = __fadd2_rn(make_float2(a1, a1), make_float2(cA.z, cA.w));
+    const float2 dz = __fadd2_rn(make_float2(a2, a2), make_float2(cB.x, cB.y));
+    const float2 d = __ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx)));
+    return __fadd2_rn(d, make_float2(af, af));
   }
 }
 
@@ -69,19 +102,21 @@ struct TopK {
 };
 
 // KM >= k1 list entries are kept; the first k1 are written out.
-template <int FORM, int QT, int KM, typename IdxT>
+// GP = candidate pairs per hit bit; a tile is 32 groups (one 32-bit mask per query) = 64*GP candidates.
+template <int FORM, int QT, int KM, int GP, typename IdxT>
 __global__ void __launch_bounds__(kThreads) knn3_kernel(const float *__restrict__ queries,
                                                         const float *__restrict__ refs, int Nq, int Nr, int k1,
                                                         float *__restrict__ vals, IdxT *__restrict__ idx,
                                                         const float *__restrict__ thr0 /*[B,Nq] or null*/) {
-  __shared__ float4 cand[kTileC];  // two float4 per candidate pair
+  constexpr int kTilePairs = 32 * GP;
+  constexpr int kTileC = 2 * kTilePairs;
+  __shared__ float4 cand[2 * kTilePairs];  // two float4 per candidate pair
   const int b = blockIdx.y, tid = threadIdx.x;
   const float *q = queries + (size_t)b * Nq * 3;
   const float *r = refs + (size_t)b * Nr * 3;
 
-  constexpr int MW = kTileC / 64;  // hit-mask words per query: one bit per candidate pair of a tile
-  float a0[QT], a1[QT], a2[QT], a3[QT], thr[QT], seed[QT];
-  unsigned mask[QT][MW];
+  float a0[QT], a1[QT], a2[QT], a3[QT], af[QT], seed[QT];
+  unsigned mask[QT];
   TopK<KM> top[QT];
 #pragma unroll
   for (int t = 0; t < QT; ++t) {
@@ -106,16 +141,15 @@ __global__ void __launch_bounds__(kThreads) knn3_kernel(const float *__restrict_
     // optional upper bound on this query's KM-th distance (knn_seed_kernel): the filter starts tight instead of
     // at +inf, so only ~KM candidates ever reach the drain instead of ~KM ln(N/KM)
     seed[t] = (thr0 != nullptr && i < Nq) ? thr0[(size_t)b * Nq + i] : CUDART_INF_F;
-    thr[t] = seed[t];
-#pragma unroll
-    for (int w = 0; w < MW; ++w) mask[t][w] = 0u;
+    af[t] = filter_addend<FORM>(a3[t], seed[t]);
+    mask[t] = 0u;
     top[t].init();
   }
 
   for (int base = 0; base < Nr; base += kTileC) {
     __syncthreads();
     // stage the tile as candidate PAIRS: A = (c0_j, c0_j1, c1_j, c1_j1), B = (c2_j, c2_j1, w_j, w_j1)
-    for (int p = tid; p < kTileC / 2; p += kThreads) {
+    for (int p = tid; p < kTilePairs; p += kThreads) {
       float c[2][4];
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
@@ -139,69 +173,73 @@ __global__ void __launch_bounds__(kThreads) knn3_kernel(const float *__restrict_
       cand[2 * p + 1] = make_float4(c[0][2], c[1][2], c[0][3], c[1][3]);
     }
     __syncthreads();
-    const int npairs = (min(kTileC, Nr - base) + 1) >> 1;
+    const int ngroups = ((min(kTileC, Nr - base) + 1) / 2 + GP - 1) / GP;
 
-    // Windows between two drains.  First tile: 4,4,8,16,32,32,32 pairs so that the thresholds tighten
+    // Windows between two drains, in groups.  First tile: 1,1,2,4,8,8,8 groups so that cold thresholds tighten
     // geometrically.  Later tiles: the whole tile in one window -- hits are rare per lane but frequent per warp
     // there, and a longer window lets several lanes insert in the same (divergent) drain iteration.
-    int p0 = 0;
-    int step = (base == 0) ? 4 : kTileC / 2;
-    while (p0 < npairs) {
-      const int cnt = min(step, npairs - p0);
-      // ---- main loop: packed distances, one threshold test per (query, candidate pair) ----------------------
+    int g0 = 0;
+    int step = (base == 0) ? 1 : 32;
+    while (g0 < ngroups) {
+      const int cnt = min(step, ngroups - g0);
+      // ---- main loop: packed filter values, sign bits OR-ed per group and shifted into the query's mask ------
+      // (after cnt shifts, bit cnt-1-g belongs to group g0+g)
+#pragma unroll 1
+      for (int g = 0; g < cnt; ++g) {
+        const float4 *cp = cand + 2 * GP * (g0 + g);
+        float4 cA[GP], cB[GP];
 #pragma unroll
-      for (int w = 0; w < MW; ++w) {
-        const int gcnt = min(32, cnt - 32 * w);
-#pragma unroll 2
-        for (int g = 0; g < gcnt; ++g) {
-          const float4 cA = cand[2 * (p0 + 32 * w + g)], cB = cand[2 * (p0 + 32 * w + g) + 1];
-          const unsigned bit = 1u << g;
+        for (int u = 0; u < GP; ++u) {
+          cA[u] = cp[2 * u];
+          cB[u] = cp[2 * u + 1];
+        }
 #pragma unroll
-          for (int t = 0; t < QT; ++t) {
-            float2 d;
-            if (FORM == HG_KNN_FORM_EXPANDED) {
-              float2 tt = __fmul2_rn(make_float2(a0[t], a0[t]), make_float2(cA.x, cA.y));
-              tt = __ffma2_rn(make_float2(a1[t], a1[t]), make_float2(cA.z, cA.w), tt);
-              tt = __ffma2_rn(make_float2(a2[t], a2[t]), make_float2(cB.x, cB.y), tt);
-              const float2 s = __fadd2_rn(make_float2(cB.z, cB.w), tt);
-              d = __fadd2_rn(s, make_float2(a3[t], a3[t]));
-            } else {
-              const float2 dx = __fadd2_rn(make_float2(a0[t], a0[t]), make_float2(cA.x, cA.y));
-              const float2 dy = __fadd2_rn(make_float2(a1[t], a1[t]), make_float2(cA.z, cA.w));
-              const float2 dz = __fadd2_rn(make_float2(a2[t], a2[t]), make_float2(cB.x, cB.y));
-              d = __ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx)));
-            }
-            if (fminf(d.x, d.y) < thr[t]) mask[t][w] |= bit;
+        for (int t = 0; t < QT; ++t) {
+          unsigned o = 0u;
+#pragma unroll
+          for (int u = 0; u < GP; ++u) {
+            const float2 e = filter_value<FORM>(a0[t], a1[t], a2[t], af[t], cA[u], cB[u]);
+            o |= __float_as_uint(e.x) | __float_as_uint(e.y);
           }
+          mask[t] = __funnelshift_l(o, mask[t], 1);
         }
       }
-      // ---- drain: each lane inserts its own hits (ascending candidate order per query) ----------------------
+      // ---- drain (divergent, rare).  Each lane walks its flagged groups in ascending order; a group is
+      // re-evaluated with the same packed filter arithmetic to find WHICH of its 2*GP candidates are below the
+      // threshold, and only those are evaluated exactly and inserted.  The insertion code (the expensive part)
+      // is thus reached once per group iteration by all lanes together, not once per candidate slot.
 #pragma unroll
       for (int t = 0; t < QT; ++t) {
-        while (true) {
-          int w = -1;
-          unsigned m = 0u;
+        unsigned m = mask[t];
+        while (m) {
+          const int pos = 31 - __clz(m);
+          m &= ~(1u << pos);
+          const int grp = g0 + cnt - 1 - pos;
+          const float4 *cp = cand + 2 * GP * grp;
+          unsigned sub = 0u;  // after 2*GP shifts, bit 2*GP-1-c belongs to candidate c of the group
 #pragma unroll
-          for (int u = MW - 1; u >= 0; --u)
-            if (mask[t][u]) {
-              w = u;
-              m = mask[t][u];
-            }
-          if (w < 0) break;
-          const int g = __ffs(m) - 1;
-#pragma unroll
-          for (int u = 0; u < MW; ++u)
-            if (u == w) mask[t][u] = m & (m - 1u);
-          const int pp = p0 + 32 * w + g;
-          const float4 cA = cand[2 * pp], cB = cand[2 * pp + 1];
-          const int j0 = base + 2 * pp;
-          top[t].push(knn_dist_exact<FORM>(a0[t], a1[t], a2[t], a3[t], cA.x, cA.z, cB.x, cB.z), j0);
-          top[t].push(knn_dist_exact<FORM>(a0[t], a1[t], a2[t], a3[t], cA.y, cA.w, cB.y, cB.w), j0 + 1);
+          for (int u = 0; u < GP; ++u) {
+            const float4 cA = cp[2 * u], cB = cp[2 * u + 1];
+            const float2 e = filter_value<FORM>(a0[t], a1[t], a2[t], af[t], cA, cB);
+            sub = __funnelshift_l(__float_as_uint(e.x), sub, 1);
+            sub = __funnelshift_l(__float_as_uint(e.y), sub, 1);
+          }
+          while (sub) {
+            const int sp = 31 - __clz(sub);
+            sub &= ~(1u << sp);
+            const int c = 2 * GP - 1 - sp;
+            const float4 cA = cp[2 * (c >> 1)], cB = cp[2 * (c >> 1) + 1];
+            const bool hi = c & 1;
+            top[t].push(knn_dist_exact<FORM>(a0[t], a1[t], a2[t], a3[t], hi ? cA.y : cA.x, hi ? cA.w : cA.z,
+                                             hi ? cB.y : cB.x, hi ? cB.w : cB.z),
+                        base + 2 * GP * grp + c);
+          }
         }
-        thr[t] = fminf(seed[t], top[t].v[KM - 1]);
+        mask[t] = 0u;
+        af[t] = filter_addend<FORM>(a3[t], fminf(seed[t], top[t].v[KM - 1]));
       }
-      p0 += cnt;
-      if (base == 0 && step < 32 && p0 >= 2 * step) step *= 2;  // 4,4,8,16,32,32,...
+      g0 += cnt;
+      if (base == 0 && step < 8 && g0 >= 2 * step) step *= 2;  // 1,1,2,4,8,8,8
     }
   }
 
@@ -225,7 +263,12 @@ int launch_qt(const float *q, const float *r, int B, int Nq, int Nr, int k1, flo
               const float *thr0, cudaStream_t stream) {
   dim3 grid((Nq + QT * kThreads - 1) / (QT * kThreads), B);
   const bool prof = hg_prof_begin(HG_PROF_KNN, stream);
-  knn3_kernel<FORM, QT, KM, IdxT><<<grid, kThreads, 0, stream>>>(q, r, Nq, Nr, k1, vals, idx, thr0);
+  // 8 candidates per hit bit (512-candidate tiles) for long candidate lists, 4 (256) for short ones, where the
+  // cheaper group re-evaluation in the drain outweighs the extra mask updates (measured cross-over ~2-4k)
+  if (Nr < 2048)
+    knn3_kernel<FORM, QT, KM, 2, IdxT><<<grid, kThreads, 0, stream>>>(q, r, Nq, Nr, k1, vals, idx, thr0);
+  else
+    knn3_kernel<FORM, QT, KM, 4, IdxT><<<grid, kThreads, 0, stream>>>(q, r, Nq, Nr, k1, vals, idx, thr0);
   hg_prof_end(HG_PROF_KNN, stream, prof);
   HG_CHECK_LAUNCH("knn3_kernel");
   return HG_OK;
