@@ -41,7 +41,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="hitgeom", choices=["hitgeom", "reference"])
-    ap.add_argument("--workload", default="c5shard", choices=["c5shard", "c1", "hitadv"])
+    ap.add_argument("--workload", default="c5shard", choices=["c5shard", "c1", "hitadv", "cwknn"])
     ap.add_argument("--clouds", type=int, default=0, help="clouds per GPU (default: workload's)")
     ap.add_argument("--points", type=int, default=0, help="points per cloud (default: workload's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -493,10 +493,146 @@ def main_hitadv(args):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------------------------------
+# The caller of BASELINE config 1: the CW-kNN attack loop (CW/kNN.py) with ChamferkNNDist on 388 x 1024-point clouds
+# against a random-init PointNet.  A "step" = one attack iteration over the batch (victim fwd/bwd -> Chamfer + kNN
+# losses fwd/bwd -> Adam -> l_inf clip).  value = cloud-iterations per second.
+# ------------------------------------------------------------------------------------------------------------
+CWKNN_METRIC = "CW-kNN attack cloud-iterations/sec"
+CWKNN_HP = dict(attack_lr=1e-3, kappa=15.0, budget=0.18)
+
+
+def cwknn_inputs(B, K, seed):
+    ori, _ = make_clouds(B, K, seed)
+    rng = np.random.default_rng(seed + 1)
+    return torch.from_numpy(ori), torch.from_numpy(rng.integers(0, 40, B))
+
+
+def cwknn_port_run(B, K, iters, device):
+    """The reference loop (oracle/cwknn_port.py + oracle/torch_port.py, bit-identical to the reference classes on CPU)."""
+    from hitgeom import adv_utils, clip_utils
+    from oracle import cwknn_port, torch_port
+    from util_models import PointNetCls
+
+    data, target = cwknn_inputs(B, K, 4321)
+    model = PointNetCls(40, seed=0)
+    torch.manual_seed(0)
+    sync = torch.cuda.synchronize if device != "cpu" else (lambda: None)
+    sync()
+    t0 = time.time()
+    cwknn_port.attack(model, data, target, adv_utils.LogitsAdvLoss(kappa=CWKNN_HP["kappa"]), torch_port.chamfer_knn_dist,
+                      clip_utils.ClipPointsLinf(budget=CWKNN_HP["budget"]), attack_lr=CWKNN_HP["attack_lr"], num_iter=iters,
+                      device=device)
+    sync()
+    return time.time() - t0
+
+
+def main_cwknn(args):
+    from util_models import PointNetCls
+
+    B, K = (args.clouds or 388), (args.points or 1024)
+    name = f"C1 caller: CW-kNN attack loop (ChamferkNNDist, l_inf clip), batch {B} x {K} points, random-init PointNet victim"
+    if args.impl == "reference":
+        if int(os.environ.get("RANK", "0")) != 0:
+            return
+        torch.set_num_threads(os.cpu_count() or 1)
+        Bc, it = 16, max(5, args.steps)
+        dt = cwknn_port_run(Bc, K, it, "cpu")
+        cb = {"value": Bc * it / dt, "unit": "cloud-iterations/s", "cores": os.cpu_count(), "kind": "port",
+              "sample": f"batch of {Bc} clouds x {K} points, {it} iterations"}
+        line = {"impl": "reference", "metric": CWKNN_METRIC, "value": cb["value"], "unit": cb["unit"], "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / it * 1e3, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": name},
+                "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": cb["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line), flush=True)
+        return
+    from hitgeom import _lib, sharding
+    from hitgeom.adv_utils import LogitsAdvLoss
+    from hitgeom.clip_utils import ClipPointsLinf
+    from hitgeom.cw_knn import CWKNN
+    from hitgeom.dist_utils import ChamferkNNDist
+
+    rank, world, local = sharding.init()
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    data, target = cwknn_inputs(B, K, 1234 + rank)
+    model = PointNetCls(40, seed=0).to(dev)
+    iters = max(20, 10 * args.steps)
+
+    def run(n_iter, graph):
+        att = CWKNN(model, LogitsAdvLoss(kappa=CWKNN_HP["kappa"]), ChamferkNNDist(), ClipPointsLinf(budget=CWKNN_HP["budget"]),
+                    attack_lr=CWKNN_HP["attack_lr"], num_iter=n_iter, graph=graph)
+        torch.manual_seed(0)
+        torch.cuda.synchronize()
+        t0 = time.time()
+        att.attack(data, target)
+        torch.cuda.synchronize()
+        return att, time.time() - t0
+
+    run(max(8, args.warmup), True)
+    run(max(8, args.warmup), False)
+    sampler = ClockSampler(local) if rank == 0 else None
+    sharding.barrier()
+    if sampler:
+        sampler.begin()
+    # two lengths: the difference removes the warm-up iterations that run eagerly before capture
+    att1, wall1 = run(iters, True)
+    att2, wall2 = run(2 * iters, True)
+    if sampler:
+        sampler.end()
+    sharding.barrier()
+    launches0 = _lib.launch_count()
+    att_e, _ = run(iters, False)
+    launches = (_lib.launch_count() - launches0) // iters
+    graph_ms = sharding.max_over_ranks((att2.loop_ms - att1.loop_ms) / iters)
+    eager_ms = sharding.max_over_ranks(att_e.loop_ms / iters)
+    e2e_ms = sharding.max_over_ranks(wall2 * 1e3 / (2 * iters))
+    clocks = sampler.stop() if sampler else {}
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+    if rank != 0:
+        return
+    line = {"metric": CWKNN_METRIC, "value": world * B / (graph_ms * 1e-3), "unit": "cloud-iterations/s", "n_gpus": world,
+            "steps": iters, "warmup": max(8, args.warmup), "ms_per_step": graph_ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": name, "batch_per_gpu": B, "points": K, "eager_ms_per_step": eager_ms,
+                       "note": "value = device time per iteration with the iteration replayed as one CUDA graph (difference of "
+                               "two attack lengths); eager_ms_per_step = same loop launched kernel by kernel; e2e = whole "
+                               "attack() call: host data in, iterations, adversarial clouds back to the host",
+                       "l2": "working set (victim activations, 388 x 1024 x 1024 floats per layer) exceeds the 126 MB L2"},
+            "clocks": clocks,
+            "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": "cloud-iterations/s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": int(data.numel() * 4 / (2 * iters)), "d2h_bytes_per_step": int(B * K * 3 * 4 / (2 * iters))},
+            "gpu_launches": int(launches),
+            "gpu_launches_note": "hitgeom kernel launches per iteration, counted on the eager run (a graph replay re-runs the same kernels without passing the counter)"}
+    if world == 1 and not args.no_cpu_baseline:
+        try:  # the reference's torch program on THIS GPU
+            n_ref = 10
+            cwknn_port_run(B, K, 3, dev)
+            per_iter = cwknn_port_run(B, K, n_ref, dev) / n_ref
+            line["reference_torch_path_on_this_gpu"] = {"value": B / per_iter, "unit": "cloud-iterations/s", "ms_per_step": per_iter * 1e3,
+                                                        "what": "oracle/cwknn_port.py + torch_port.py (the reference's tensor program) on cuda:0, batch %d" % B}
+        except Exception as e:
+            line["reference_torch_path_on_this_gpu"] = {"value": None, "what": f"failed: {e}"}
+        try:
+            torch.set_num_threads(os.cpu_count() or 1)
+            Bc, it = 16, 5
+            dt = cwknn_port_run(Bc, K, it, "cpu")
+            line["cpu_baseline"] = {"value": Bc * it / dt, "unit": "cloud-iterations/s", "cores": os.cpu_count(), "kind": "port",
+                                    "sample": f"batch of {Bc} clouds x {K} points, {it} iterations"}
+        except Exception as e:
+            line["cpu_baseline"] = {"value": None, "unit": "cloud-iterations/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
+    print(json.dumps(line), flush=True)
+
+
 if __name__ == "__main__":
     a = parse()
     if a.workload == "hitadv":
         main_hitadv(a)
+    elif a.workload == "cwknn":
+        main_cwknn(a)
     elif a.impl == "reference":
         main_reference(a)
     else:

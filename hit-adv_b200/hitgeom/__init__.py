@@ -13,6 +13,9 @@ meaning and error behaviour), calling hand-written CUDA kernels through the C AB
     hitgeom.sharding       instance-sharded multi-GPU driver (one process per GPU, NCCL all-gather at the end)
     hitgeom.hit_adv        HiT_ADV attacker with the fused deformation kernel and on-device bookkeeping
                            (ShapeAttack/HiT_ADV.py; SURVEY.md 8f "next" rows #1, #2)
+    hitgeom.cw_knn         CWKNN / CWUKNN attack loops, sync-free and CUDA-graph replayable (CW/kNN.py, CW/UKNN.py)
+    hitgeom.clip_utils     ClipPointsL2 / ClipPointsLinf / ProjectInnerPoints / ProjectInnerClipLinf (util/clip_utils.py)
+    hitgeom.adv_utils      LogitsAdvLoss / UntargetedLogitsAdvLoss / CrossEntropyAdvLoss           (util/adv_utils.py)
 
 There is no CPU path: importing works anywhere (so the build can be checked without a GPU), but every
 operator raises unless its tensors live on a CUDA device and libhitgeom.so is present.
@@ -28,6 +31,6 @@ def __getattr__(name):
     import importlib
 
     if name in ("set_distance", "dist_utils", "pointnet2_ops", "model_seams", "pytorch3d_ops", "functional",
-                "sharding", "hit_adv"):
+                "sharding", "hit_adv", "cw_knn", "clip_utils", "adv_utils"):
         return importlib.import_module(f".{name}", __name__)
     raise AttributeError(name)

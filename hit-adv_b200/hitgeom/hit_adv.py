@@ -23,23 +23,10 @@ import torch.nn.functional as F_t
 import torch.optim as optim
 
 from . import functional as F
+from .adv_utils import UntargetedLogitsAdvLoss  # noqa: F401  (re-exported: util/adv_utils.py:38-67)
 from .dist_utils import ChamferDist
 from .model_seams import index_points
 from .pytorch3d_ops import knn_gather, knn_points
-
-
-class UntargetedLogitsAdvLoss(torch.nn.Module):
-    """util/adv_utils.py:38-67 (device-agnostic)."""
-
-    def __init__(self, kappa=0.):
-        super().__init__()
-        self.kappa = kappa
-
-    def forward(self, logits, targets):
-        one_hot = torch.zeros_like(logits).scatter_(1, targets.view(-1, 1).long(), 1.0)
-        real = torch.sum(one_hot * logits, dim=1)
-        other = torch.max((1. - one_hot) * logits - one_hot * 10000., dim=1)[0]
-        return torch.clamp(real - other + self.kappa, min=0.).mean()
 
 
 class HiT_ADV:

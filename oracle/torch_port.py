@@ -17,8 +17,8 @@ def pairwise(x, y):
     xx = torch.bmm(x, x.transpose(2, 1))
     yy = torch.bmm(y, y.transpose(2, 1))
     zz = torch.bmm(x, y.transpose(2, 1))
-    ix = torch.arange(x.shape[1])
-    iy = torch.arange(y.shape[1])
+    ix = torch.arange(x.shape[1], device=x.device)
+    iy = torch.arange(y.shape[1], device=y.device)
     rx = xx[:, ix, ix].unsqueeze(1).expand_as(zz.transpose(2, 1))
     ry = yy[:, iy, iy].unsqueeze(1).expand_as(zz)
     return rx.transpose(2, 1) + ry - 2 * zz
@@ -40,8 +40,8 @@ def _pick(l1, l2, method):
 
 def _weighted(loss, weights, batch_avg):
     if weights is None:
-        weights = torch.ones(loss.shape[0])
-    loss = loss * weights.float()
+        weights = torch.ones(loss.shape[0], device=loss.device)
+    loss = loss * weights.float().to(loss.device)
     return loss.mean() if batch_avg else loss
 
 

@@ -147,3 +147,27 @@ def test_p2_three_nn_interpolate_match_reference_kernel(golden, oracle):
     d2, idx = oracle.p2_three_nn(g["nn_unknown"], g["nn_known"])
     assert np.array_equal(d2, g["nn_dist2"]) and np.array_equal(idx, g["nn_idx"])
     assert np.array_equal(oracle.p2_three_interpolate(g["ti_feats"], g["nn_idx"], g["ti_w"]), g["ti_out"])
+
+
+# ---- CW-kNN attack loops: the oracle's restatement reproduces the unmodified reference classes bit for bit ----------
+def test_cwknn_port_reproduces_reference_attackers(golden):
+    import torch
+    from hitgeom import adv_utils, clip_utils
+    from oracle import cwknn_port, torch_port as tp
+    from util_models import TinyPointNet
+
+    g = golden("cwknn_ref")
+    hp = {k[3:]: g[k].item() for k in g.files if k.startswith("hp_")}
+    kw = dict(attack_lr=hp["attack_lr"], num_iter=int(hp["num_iter"]))
+    model = TinyPointNet(40, seed=int(hp["model_seed"]))  # (module construction draws from the global generator)
+    torch.manual_seed(int(hp["seed"]))
+    adv, succ = cwknn_port.attack(model, torch.from_numpy(g["pts"]),
+                                  torch.from_numpy(g["knn_target"]), adv_utils.LogitsAdvLoss(kappa=hp["kappa"]),
+                                  tp.chamfer_knn_dist, clip_utils.ClipPointsLinf(budget=hp["budget"]), **kw)
+    assert np.array_equal(adv, g["knn_adv"]) and succ == int(g["knn_success"])
+    data6 = torch.from_numpy(np.concatenate([g["pts"], g["nrm"]], axis=-1))
+    torch.manual_seed(int(hp["seed"]))
+    adv, succ = cwknn_port.attack(model, data6, torch.from_numpy(g["label"]),
+                                  adv_utils.UntargetedLogitsAdvLoss(kappa=hp["kappa"]), tp.chamfer_knn_dist,
+                                  clip_utils.ProjectInnerClipLinf(budget=hp["budget"]), untargeted=True, **kw)
+    assert np.array_equal(adv, g["uknn_adv"]) and succ == int(g["uknn_success"])
