@@ -1,0 +1,204 @@
+// hg_edge.cu -- DGCNN edge features (model/dgcnn_cls.py:16-43 get_graph_feature), forward and backward.
+//
+//   out[b, c,     n, t] = x[b, c, idx[b,n,t]] - x[b, c, n]          c < C
+//   out[b, C + c, n, t] = x[b, c, n]
+//
+// The reference builds this with an index gather on a transposed copy, a k-fold `repeat`, a `cat` and a
+// `permute(...).contiguous()`: four full-size [B,N,k,2C] tensors are written and re-read (671 MB each at
+// B=32, C=128, N=1024, k=20) and autograd keeps two of them.  Here the output is written once, straight in its final
+// layout; nothing else of that size exists.  HBM-bound: algorithmic bytes = the output (8 B per edge per channel
+// forward; backward reads the same amount once).
+//
+// Backward:  grad_x[b,c,n] = sum_t (g[b,C+c,n,t] - g[b,c,n,t])  +  sum_{(m,t): idx[b,m,t] = n} g[b,c,m,t]
+// The reference's second sum is an `index_put_(accumulate=True)` with floating-point atomics (run-to-run rounding
+// differences); here it is a walk over a CSR reverse map in ascending edge order: deterministic.
+#include "hg_common.cuh"
+
+namespace {
+
+// ---- forward: one CTA row per (b,c) plane, the plane's N source values staged in shared memory ------------------
+template <bool VEC4>
+__global__ void __launch_bounds__(256) edge_feature_kernel(const float *__restrict__ x,
+                                                           const long long *__restrict__ idx, int C, int N, int k,
+                                                           long long planes, float *__restrict__ out) {
+  extern __shared__ float plane[];
+  const int E = N * k;
+  for (long long bc = blockIdx.y; bc < planes; bc += gridDim.y) {
+    const long long b = bc / C;
+    const int c = (int)(bc % C);
+    const float *src = x + (size_t)bc * N;
+    const long long *id = idx + (size_t)b * E;
+    float *dstA = out + ((size_t)b * 2 * C + c) * E;
+    float *dstB = dstA + (size_t)C * E;
+    __syncthreads();
+    for (int i = threadIdx.x; i < N; i += 256) plane[i] = __ldg(src + i);
+    __syncthreads();
+    if (VEC4) {  // k % 4 == 0: the four edges of a float4 share their centre point
+      for (int e = (blockIdx.x * 256 + threadIdx.x) * 4; e < E; e += gridDim.x * 1024) {
+        const longlong2 i01 = *reinterpret_cast<const longlong2 *>(id + e);
+        const longlong2 i23 = *reinterpret_cast<const longlong2 *>(id + e + 2);
+        const float ctr = plane[e / k];
+        float4 a;
+        a.x = plane[i01.x] - ctr;
+        a.y = plane[i01.y] - ctr;
+        a.z = plane[i23.x] - ctr;
+        a.w = plane[i23.y] - ctr;
+        __stcs(reinterpret_cast<float4 *>(dstA + e), a);  // streaming: consumed by the next layer, not here
+        __stcs(reinterpret_cast<float4 *>(dstB + e), make_float4(ctr, ctr, ctr, ctr));
+      }
+    } else {
+      for (int e = blockIdx.x * 256 + threadIdx.x; e < E; e += gridDim.x * 256) {
+        const float ctr = plane[e / k];
+        dstA[e] = plane[id[e]] - ctr;
+        dstB[e] = ctr;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) edge_keys_kernel(const long long *__restrict__ idx, long long total, int N,
+                                                        int *__restrict__ keys) {
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total;
+       g += (long long)gridDim.x * blockDim.x) {
+    const long long a = idx[g];
+    keys[g] = (a >= 0 && a < N) ? (int)a : -1;
+  }
+}
+
+// ---- backward: one CTA per (b,c) plane.  Thread n streams row n of both halves (k contiguous floats: a warp
+// covers 32*k contiguous floats), keeps sum_t (gB - gA) in a register and parks the gA row in shared memory; after
+// a barrier the incoming edges are summed from shared memory in ascending edge order.
+template <bool STAGED>
+__global__ void __launch_bounds__(256) edge_feature_grad_kernel(const float *__restrict__ g,
+                                                                const int *__restrict__ off,
+                                                                const int *__restrict__ list, int C, int N, int k,
+                                                                long long planes, float *__restrict__ grad_x) {
+  extern __shared__ float sA[];  // STAGED: [N*k] the gA plane
+  const int E = N * k;
+  const bool vec = (k & 3) == 0;
+  for (long long bc = blockIdx.x; bc < planes; bc += gridDim.x) {
+    const long long b = bc / C;
+    const int c = (int)(bc % C);
+    const float *gA = g + ((size_t)b * 2 * C + c) * E;
+    const float *gB = gA + (size_t)C * E;
+    const int *o = off + (size_t)b * (N + 1);
+    const int *l = list + (size_t)b * E;
+    float *dst = grad_x + (size_t)bc * N;
+    __syncthreads();
+    for (int n0 = 0; n0 < N; n0 += 256) {
+      const int n = n0 + threadIdx.x;
+      float own = 0.f;
+      if (n < N) {
+        const float *ra = gA + (size_t)n * k, *rb = gB + (size_t)n * k;
+        if (vec) {
+          for (int t = 0; t < k; t += 4) {
+            const float4 a = __ldcs(reinterpret_cast<const float4 *>(ra + t));
+            const float4 bb = __ldcs(reinterpret_cast<const float4 *>(rb + t));
+            own += (bb.x - a.x);
+            own += (bb.y - a.y);
+            own += (bb.z - a.z);
+            own += (bb.w - a.w);
+            if (STAGED) *reinterpret_cast<float4 *>(sA + (size_t)n * k + t) = a;
+          }
+        } else {
+          for (int t = 0; t < k; ++t) {
+            const float a = ra[t];
+            own += (rb[t] - a);
+            if (STAGED) sA[(size_t)n * k + t] = a;
+          }
+        }
+      }
+      if (!STAGED && n < N) {  // plane too large for shared memory: gather from global (L2)
+        float acc = own;
+        for (int q = o[n]; q < o[n + 1]; ++q) acc += gA[l[q]];
+        dst[n] = acc;
+      }
+      if (STAGED && n < N) dst[n] = own;  // finished below
+    }
+    if (STAGED) {
+      __syncthreads();
+      for (int n = threadIdx.x; n < N; n += 256) {
+        float acc = dst[n];
+        for (int q = o[n]; q < o[n + 1]; ++q) acc += sA[l[q]];
+        dst[n] = acc;
+      }
+    }
+  }
+}
+
+}  // namespace
+
+// dgcnn_cls.py:16-43 (feature build only; the neighbour search is hg_knn_self_f32 / model_seams.knn)
+HG_API int hg_edge_feature_f32(const float *x, const int64_t *idx, int B, int C, int N, int k, float *out,
+                               hgStream stream_) {
+  cudaStream_t stream = hg_stream(stream_);
+  HG_REQUIRE(x && idx && out, HG_E_BADARG, "edge_feature: null pointer");
+  HG_REQUIRE(B > 0 && C > 0 && N > 0 && k > 0, HG_E_BADARG, "edge_feature: sizes must be positive");
+  HG_REQUIRE((long long)N * k < (1LL << 31), HG_E_UNSUPPORTED, "edge_feature: N*k too large");
+  HG_REQUIRE((size_t)N * sizeof(float) <= 200 * 1024, HG_E_UNSUPPORTED, "edge_feature: N=%d too large for the staged plane", N);
+  const long long planes = (long long)B * C;
+  const int E = N * k;
+  const bool vec = (k % 4 == 0) && ((reinterpret_cast<uintptr_t>(idx) | reinterpret_cast<uintptr_t>(out)) % 16 == 0);
+  const int per_block = vec ? 1024 : 256;
+  int gx = (E + per_block - 1) / per_block;
+  const int gx_cap = planes >= 4LL * hg_sm_count() ? 1 : 4;  // one CTA per plane once the planes fill the machine
+  if (gx > gx_cap) gx = gx_cap;
+  const int gy = (int)(planes < 65535 ? planes : 65535);
+  const size_t smem = (size_t)N * sizeof(float);
+  const bool prof = hg_prof_begin(HG_PROF_GROUP, stream);
+  if (vec) {
+    if (smem > 48 * 1024)
+      HG_CUDA(cudaFuncSetAttribute(edge_feature_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    edge_feature_kernel<true><<<dim3(gx, gy), 256, smem, stream>>>(x, (const long long *)idx, C, N, k, planes, out);
+  } else {
+    if (smem > 48 * 1024)
+      HG_CUDA(cudaFuncSetAttribute(edge_feature_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    edge_feature_kernel<false><<<dim3(gx, gy), 256, smem, stream>>>(x, (const long long *)idx, C, N, k, planes, out);
+  }
+  hg_prof_end(HG_PROF_GROUP, stream, prof);
+  HG_CHECK_LAUNCH("edge_feature_kernel");
+  return HG_OK;
+}
+
+HG_API size_t hg_edge_feature_grad_workspace_bytes(int B, int N, int k) {
+  if (B <= 0 || N <= 0 || k <= 0) return 0;
+  return hg_align((size_t)B * N * k * sizeof(int)) + hg_csr_workspace_bytes(B, N, N * k);
+}
+
+HG_API int hg_edge_feature_grad_f32(const float *grad_out, const int64_t *idx, int B, int C, int N, int k,
+                                    float *grad_x, void *workspace, size_t workspace_bytes, hgStream stream_) {
+  cudaStream_t stream = hg_stream(stream_);
+  HG_REQUIRE(grad_out && idx && grad_x, HG_E_BADARG, "edge_feature_grad: null pointer");
+  HG_REQUIRE(B > 0 && C > 0 && N > 0 && k > 0, HG_E_BADARG, "edge_feature_grad: sizes must be positive");
+  HG_REQUIRE((long long)N * k < (1LL << 31), HG_E_UNSUPPORTED, "edge_feature_grad: N*k too large");
+  HG_REQUIRE(workspace && workspace_bytes >= hg_edge_feature_grad_workspace_bytes(B, N, k), HG_E_WORKSPACE,
+             "edge_feature_grad: workspace too small");
+  const int E = N * k;
+  int *keys = (int *)workspace;
+  void *csr_ws = (char *)workspace + hg_align((size_t)B * E * sizeof(int));
+  const long long te = (long long)B * E;
+  long long kb = (te + 255) / 256;
+  if (kb > (long long)hg_sm_count() * 32) kb = (long long)hg_sm_count() * 32;
+  edge_keys_kernel<<<(int)kb, 256, 0, stream>>>((const long long *)idx, te, N, keys);
+  HG_CHECK_LAUNCH("edge_keys_kernel");
+  HgCsr csr;
+  int rc = hg_csr_build_unordered(keys, B, E, N, csr_ws, hg_csr_workspace_bytes(B, N, E), &csr, stream);
+  if (rc) return rc;
+  rc = hg_csr_sort_segments(&csr, B, E, N, stream);  // (a no-op on the already-sorted small-problem path)
+  if (rc) return rc;
+  const long long planes = (long long)B * C;
+  const size_t smem = (size_t)E * sizeof(float);
+  const bool staged = smem <= 200 * 1024;
+  long long grid = planes;
+  const long long cap = (long long)hg_sm_count() * 8;
+  if (grid > cap) grid = cap;
+  if (staged) {
+    if (smem > 48 * 1024)
+      HG_CUDA(cudaFuncSetAttribute(edge_feature_grad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    edge_feature_grad_kernel<true><<<(int)grid, 256, smem, stream>>>(grad_out, csr.off, csr.list, C, N, k, planes, grad_x);
+  } else {
+    edge_feature_grad_kernel<false><<<(int)grid, 256, 0, stream>>>(grad_out, csr.off, csr.list, C, N, k, planes, grad_x);
+  }
+  HG_CHECK_LAUNCH("edge_feature_grad_kernel");
+  return HG_OK;
+}

@@ -45,6 +45,9 @@ _SIGNATURES = {
     "hg_index_points_grad_f32": (I, [P, P, I, I, I, I, P, P, Z, P]),
     "hg_hitadv_deform_fwd_f32": (I, [P, P, P, P, I, I, I, P, P, P]),
     "hg_hitadv_deform_bwd_f32": (I, [P, P, P, P, P, P, P, I, I, I, P, P, P]),
+    "hg_edge_feature_f32": (I, [P, P, I, I, I, I, P, P]),
+    "hg_edge_feature_grad_workspace_bytes": (Z, [I, I, I]),
+    "hg_edge_feature_grad_f32": (I, [P, P, I, I, I, I, P, P, Z, P]),
     "hg_p2_gather_points": (I, [I, I, I, I, P, P, P, P]),
     "hg_p2_scatter_workspace_bytes": (Z, [I, I, I]),
     "hg_p2_gather_points_grad": (I, [I, I, I, I, P, P, P, P, Z, P]),

@@ -5,7 +5,7 @@ No arithmetic on point data happens in Python/PyTorch here; torch only allocates
 import torch
 
 from . import _lib
-from ._lib import check, lib, ptr, require, stream_ptr, workspace
+from ._lib import HitgeomError, check, lib, ptr, require, stream_ptr, workspace
 
 MODE_CHAMFER, MODE_HAUSDORFF = 0, 1
 
@@ -274,6 +274,39 @@ class DeformFn(torch.autograd.Function):
 
 def hitadv_deform(ori, centers, perturb, delta):
     return DeformFn.apply(ori, centers, perturb, delta)
+
+
+class EdgeFeatureFn(torch.autograd.Function):
+    """DGCNN edge features (dgcnn_cls.py:16-43): x [B,C,N], idx [B,N,k] int64 -> [B,2C,N,k] = cat(x_nbr - x, x)."""
+
+    @staticmethod
+    def forward(ctx, x, idx):
+        xc = x.detach().contiguous()
+        require(xc, "x")
+        ic = idx.contiguous()
+        if ic.dtype != torch.int64 or not ic.is_cuda:
+            raise HitgeomError("edge_feature: idx must be a CUDA int64 tensor [B,N,k]")
+        B, C, N = xc.shape
+        k = ic.shape[2]
+        out = torch.empty((B, 2 * C, N, k), dtype=torch.float32, device=xc.device)
+        check(lib().hg_edge_feature_f32(ptr(xc), ptr(ic), B, C, N, k, ptr(out), stream_ptr()), "hg_edge_feature_f32")
+        ctx.saved = (ic, C)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        idx, C = ctx.saved
+        g = grad_out.to(torch.float32).contiguous()
+        B, _, N, k = g.shape
+        grad = torch.empty((B, C, N), dtype=torch.float32, device=g.device)
+        ws = workspace(lib().hg_edge_feature_grad_workspace_bytes(B, N, k), g.device)
+        check(lib().hg_edge_feature_grad_f32(ptr(g), ptr(idx), B, C, N, k, ptr(grad), ptr(ws), ws.numel(), stream_ptr()),
+              "hg_edge_feature_grad_f32")
+        return grad, None
+
+
+def edge_feature(x, idx):
+    return EdgeFeatureFn.apply(x, idx)
 
 
 def tune_nn_bidir(T=0, RB=0):

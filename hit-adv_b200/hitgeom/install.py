@@ -9,7 +9,7 @@ What gets registered / patched:
   * after the reference modules are imported, `patch_reference()` swaps
         util.set_distance.chamfer / hausdorff, util.dist_utils.{chamfer,hausdorff,ChamferDist,HausdorffDist,
         KNNDist,ChamferkNNDist}.forward, model.pointnet2_utils.{square_distance,index_points,
-        farthest_point_sample,query_ball_point}, model.dgcnn_cls.knn
+        farthest_point_sample,query_ball_point}, model.dgcnn_cls.{knn,get_graph_feature}
     for the kernel-backed versions.  Callers (CW/*.py, ShapeAttack/HiT_ADV.py, util/other_utils.py) keep
     constructing and calling the same classes.
 """
@@ -63,5 +63,6 @@ def patch_reference():
     m = sys.modules.get("model.dgcnn_cls")
     if m is not None:
         m.knn = ms.knn
+        m.get_graph_feature = ms.get_graph_feature
         patched.append("model.dgcnn_cls")
     return patched

@@ -5,6 +5,7 @@
   model/pointnet2_utils.py:63-84   farthest_point_sample(xyz, npoint)        (random start: torch.randint)
   model/pointnet2_utils.py:87-107  query_ball_point(radius, nsample, xyz, new_xyz)
   model/dgcnn_cls.py:7-13          knn(x, k)                                 (x is channel-major [B,C,N])
+  model/dgcnn_cls.py:16-43         get_graph_feature(x, k=20, idx=None, dim9=False)  (differentiable in x)
 
 Same signatures, dtypes (int64 indices) and semantics, so `hitgeom.install()` can rebind them into the
 reference's module globals and PointNet++ SSG / DGCNN run unchanged (`sample_and_group` and
@@ -49,3 +50,13 @@ def knn(x, k):
     pc = x.detach().transpose(2, 1).contiguous()  # kernels are point-major
     _, idx = F.knn_self(pc, int(k), want_vals=False)
     return idx.long()
+
+
+def get_graph_feature(x, k=20, idx=None, dim9=False):
+    """x [B,C,N] -> edge features [B,2C,N,k] = cat(x[idx] - x, x) (dgcnn_cls.py:16-43), one kernel instead of
+    gather + repeat + cat + permute().contiguous(); kNN on the features (or on channels 6: when `dim9`)."""
+    batch_size, num_points = x.size(0), x.size(2)
+    x = x.view(batch_size, -1, num_points)
+    if idx is None:
+        idx = knn(x if not dim9 else x[:, 6:], k=k)
+    return F.edge_feature(x, idx)

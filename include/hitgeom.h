@@ -174,6 +174,19 @@ int hg_hitadv_deform_bwd_f32(const float *ori, const float *centers, const float
                              const float *out, const float *deno, const float *grad_out, int B, int K, int J,
                              float *grad_perturb, float *grad_delta, hgStream stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Row a9' / "next" row 8f#3: DGCNN edge features, model/dgcnn_cls.py:16-43 get_graph_feature (after its kNN).
+ *   x [B,C,N] channel-first features, idx [B,N,k] int64 neighbour indices (as torch.topk / model_seams.knn give them)
+ *   out [B,2C,N,k]:  out[b,c,n,t] = x[b,c,idx[b,n,t]] - x[b,c,n],   out[b,C+c,n,t] = x[b,c,n]
+ * written once in its final layout (the reference goes through gather + repeat + cat + permute().contiguous()).
+ * The backward sums the incoming edges through a CSR reverse map in ascending edge order (deterministic; the
+ * reference's index_put_(accumulate=True) uses floating-point atomics).
+ * ------------------------------------------------------------------------------------------------------- */
+int hg_edge_feature_f32(const float *x, const int64_t *idx, int B, int C, int N, int k, float *out, hgStream stream);
+size_t hg_edge_feature_grad_workspace_bytes(int B, int N, int k);
+int hg_edge_feature_grad_f32(const float *grad_out, const int64_t *idx, int B, int C, int N, int k, float *grad_x,
+                             void *workspace, size_t workspace_bytes, hgStream stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -88,3 +88,16 @@ def step_cd_hd_knn(adv, ori):
             + knn_dist(a, batch_avg=False)).sum()
     loss.backward()
     return loss.detach(), a.grad
+
+
+def get_graph_feature(x, idx):
+    """model/dgcnn_cls.py:16-43 after the neighbour search: x [B,C,N], idx [B,N,k] -> [B,2C,N,k] = cat(x[idx] - x, x),
+    the same tensor program (flat gather on the transposed copy, repeat, cat, permute) on whatever device x is on.
+    Pinned against tests/golden/dgcnn_edge.npz (bit-exact, forward and autograd gradient, on this container's CPU)."""
+    B, C, N = x.shape
+    k = idx.shape[2]
+    flat = (idx + torch.arange(0, B, device=x.device).view(-1, 1, 1) * N).view(-1)
+    xt = x.transpose(2, 1).contiguous()
+    feature = xt.view(B * N, -1)[flat, :].view(B, N, k, C)
+    xr = xt.view(B, N, 1, C).repeat(1, 1, k, 1)
+    return torch.cat((feature - xr, xr), dim=3).permute(0, 3, 1, 2).contiguous()

@@ -171,3 +171,18 @@ def test_cwknn_port_reproduces_reference_attackers(golden):
                                   adv_utils.UntargetedLogitsAdvLoss(kappa=hp["kappa"]), tp.chamfer_knn_dist,
                                   clip_utils.ProjectInnerClipLinf(budget=hp["budget"]), untargeted=True, **kw)
     assert np.array_equal(adv, g["uknn_adv"]) and succ == int(g["uknn_success"])
+
+
+def test_edge_feature_port_matches_reference(golden):
+    import torch
+    from oracle import torch_port as tp
+
+    g = golden("dgcnn_edge")
+    for tag, C in (("a", 3), ("b", 64), ("c", 5)):
+        x = torch.from_numpy(g[f"{tag}_x"]).requires_grad_()
+        gen = torch.Generator().manual_seed(70 + C)
+        assert torch.equal(torch.randn(x.shape, generator=gen), x.detach())  # the fixture's own draw
+        feat = tp.get_graph_feature(x, torch.from_numpy(g[f"{tag}_idx"]))
+        assert np.array_equal(feat.detach().numpy(), g[f"{tag}_feat"]), tag
+        (feat * torch.randn(feat.shape, generator=gen)).sum().backward()
+        assert np.array_equal(x.grad.numpy(), g[f"{tag}_grad"]), tag
