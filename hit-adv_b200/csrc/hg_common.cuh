@@ -114,8 +114,6 @@ int hg_csr_build(const int *keys, int B, int E, int N, void *workspace, size_t w
 // hg_csr_next() to get ascending edge order (deterministic sums without a stable sort).
 int hg_csr_build_unordered(const int *keys, int B, int E, int N, void *workspace, size_t workspace_bytes, HgCsr *out,
                            cudaStream_t stream);
-// sorts every segment of an (unordered) CSR ascending in place: for consumers that walk each segment many times
-int hg_csr_sort_segments(const HgCsr *csr, int B, int E, int N, cudaStream_t stream);
 // smallest entry of list[p0..p1) that is greater than `last` (INT_MAX if none)
 __device__ __forceinline__ int hg_csr_next(const int *__restrict__ list, int p0, int p1, int last) {
   int best = 0x7fffffff;

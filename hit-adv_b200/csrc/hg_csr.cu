@@ -211,38 +211,3 @@ int hg_csr_build_unordered(const int *keys, int B, int E, int N, void *workspace
   out->list = list;
   return HG_OK;
 }
-
-// ---- in-place ascending sort of every segment (for consumers that walk each segment many times) -----------------
-namespace {
-__global__ void __launch_bounds__(256) csr_sort_segments_kernel(const int *__restrict__ off_all,
-                                                                int *__restrict__ list_all, long long total, int N,
-                                                                int E) {
-  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total;
-       g += (long long)gridDim.x * blockDim.x) {
-    const long long b = g / N;
-    const int key = (int)(g % N);
-    const int *off = off_all + b * (N + 1);
-    int *l = list_all + b * E;
-    const int p0 = off[key], p1 = off[key + 1];
-    for (int q = p0 + 1; q < p1; ++q) {  // insertion sort: segments are short (mean E/N)
-      const int v = l[q];
-      int r = q - 1;
-      while (r >= p0 && l[r] > v) {
-        l[r + 1] = l[r];
-        --r;
-      }
-      l[r + 1] = v;
-    }
-  }
-}
-}  // namespace
-
-int hg_csr_sort_segments(const HgCsr *csr, int B, int E, int N, cudaStream_t stream) {
-  const long long total = (long long)B * N;
-  long long blocks = (total + 255) / 256;
-  const long long cap = (long long)hg_sm_count() * 16;
-  if (blocks > cap) blocks = cap;
-  csr_sort_segments_kernel<<<(int)blocks, 256, 0, stream>>>(csr->off, csr->list, total, N, E);
-  HG_CHECK_LAUNCH("csr_sort_segments_kernel");
-  return HG_OK;
-}

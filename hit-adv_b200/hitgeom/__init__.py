@@ -16,6 +16,8 @@ meaning and error behaviour), calling hand-written CUDA kernels through the C AB
     hitgeom.cw_knn         CWKNN / CWUKNN attack loops, sync-free and CUDA-graph replayable (CW/kNN.py, CW/UKNN.py)
     hitgeom.clip_utils     ClipPointsL2 / ClipPointsLinf / ProjectInnerPoints / ProjectInnerClipLinf (util/clip_utils.py)
     hitgeom.adv_utils      LogitsAdvLoss / UntargetedLogitsAdvLoss / CrossEntropyAdvLoss           (util/adv_utils.py)
+    hitgeom.eval_metrics   uniform_loss, kNN_smoothing_loss, CurvStdDist -- eval_ASR's per-batch metrics
+                           (FGM/GeoA3_args.py:240-302, util/dist_utils.py:464-495)
 
 There is no CPU path: importing works anywhere (so the build can be checked without a GPU), but every
 operator raises unless its tensors live on a CUDA device and libhitgeom.so is present.
@@ -31,6 +33,6 @@ def __getattr__(name):
     import importlib
 
     if name in ("set_distance", "dist_utils", "pointnet2_ops", "model_seams", "pytorch3d_ops", "functional",
-                "sharding", "hit_adv", "cw_knn", "clip_utils", "adv_utils"):
+                "sharding", "hit_adv", "cw_knn", "clip_utils", "adv_utils", "eval_metrics"):
         return importlib.import_module(f".{name}", __name__)
     raise AttributeError(name)

@@ -25,6 +25,7 @@ import torch.optim as optim
 from . import functional as F
 from .adv_utils import UntargetedLogitsAdvLoss  # noqa: F401  (re-exported: util/adv_utils.py:38-67)
 from .dist_utils import ChamferDist
+from .eval_metrics import kappa_and_neighbours, kappa_std
 from .model_seams import index_points
 from .pytorch3d_ops import knn_gather, knn_points
 
@@ -61,20 +62,11 @@ class HiT_ADV:
     def _normalize(v, p=2, dim=1, eps=1e-12):
         return v / v.norm(p, dim, keepdim=True).clamp(min=eps).expand_as(v)
 
-    def _kappa(self, pc, normal, k):
-        pts = pc.permute(0, 2, 1).contiguous()
-        knn = knn_points(pts, pts, K=k + 1)
-        nn_pts = knn_gather(pts, knn.idx).permute(0, 3, 1, 2)[:, :, :, 1:].contiguous()  # [B,3,N,k]
-        vectors = self._normalize(nn_pts - pc.unsqueeze(3))
-        return torch.abs((vectors * normal.unsqueeze(3)).sum(1)).mean(2), knn.idx
-
     def _get_kappa_ori(self, pc, normal, k=2):
-        return self._kappa(pc, normal, k)[0]
+        return kappa_and_neighbours(pc, normal, k)[0]
 
     def _get_kappa_std_ori(self, pc, normal, k=10):
-        kappa, idx = self._kappa(pc, normal, k)
-        nn_kappa = knn_gather(kappa.unsqueeze(2).contiguous(), idx).permute(0, 3, 1, 2)[:, :, :, 1:].contiguous()
-        return torch.std(nn_kappa.squeeze(1), dim=2)
+        return kappa_std(pc, normal, k)
 
     def transformation_loss(self, adv_data, perturb_mat, gauss_delta, batch_avg=True):
         if batch_avg:

@@ -118,6 +118,31 @@ def main():
             return (-xx - inner - xx.transpose(2, 1)).topk(k=20, dim=-1)[1]
 
         row(f"DGCNN knn B=32 C={C} N=1024 k=20", t_new, timeit(ref_knn), extra={"pair_evals_per_s": 32 * 1024 * 1024 / t_new * 1e3, "ref": "torch matmul+topk on the same GPU"})
+    # DGCNN edge features (get_graph_feature after its kNN), the four layers of config 4
+    from oracle import torch_port as tp
+
+    for C in (3, 64, 128):
+        Bq, Nq, kq = 32, 1024, 20
+        x = torch.randn(Bq, C, Nq, device="cuda")
+        idx = ms.knn(x, kq)
+        by = 4 * Bq * (C * Nq + 2 * C * Nq * kq) + 8 * Bq * Nq * kq
+        t_new = timeit(lambda: F.edge_feature(x, idx), flush=flush)
+        t_ref = timeit(lambda: tp.get_graph_feature(x, idx), flush=flush)
+        row(f"edge_feature B={Bq} C={C} N={Nq} k={kq}", t_new, t_ref, bytes_alg=by, extra={"ref": "reference tensor program (gather+repeat+cat+permute) on the same GPU"})
+        go = torch.randn(Bq, 2 * C, Nq, kq, device="cuda")
+        xg = x.clone().requires_grad_()
+
+        def bwd_new():
+            xg.grad = None
+            F.edge_feature(xg, idx).backward(go)
+
+        def bwd_ref():
+            xg.grad = None
+            tp.get_graph_feature(xg, idx).backward(go)
+
+        t_new_fb, t_ref_fb = timeit(bwd_new, flush=flush), timeit(bwd_ref, flush=flush)
+        row(f"edge_feature fwd+bwd B={Bq} C={C} N={Nq} k={kq}", t_new_fb, t_ref_fb, bytes_alg=2 * by,
+            extra={"ref": "reference tensor program + autograd on the same GPU"})
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump({"hbm_peak_gbs_measured": hbm, "results": res}, open(os.path.join(ROOT, "gpurun_out", "bench_ops.json"), "w"), indent=1)
 
