@@ -295,22 +295,34 @@ def main_hitgeom(args):
     clocks = sampler.stop() if sampler else {}
 
     # ---- end-to-end: host buffers in, gradient + loss back to the host, every step ---------------------------
-    def e2e_step():
-        with torch.no_grad():
-            adv_d.copy_(adv_h, non_blocking=True)
-            ori_d.copy_(ori_h, non_blocking=True)
-        loss = fwd_bwd()
-        grad_h.copy_(adv_d.grad, non_blocking=True)
-        return float(loss.item())
+    if args.workload == "c1":
+        def e2e_step():
+            with torch.no_grad():
+                adv_d.copy_(adv_h, non_blocking=True)
+                ori_d.copy_(ori_h, non_blocking=True)
+            loss = fwd_bwd()
+            grad_h.copy_(adv_d.grad, non_blocking=True)
+            return float(loss.item())
+    else:
+        # the C ABI's host-buffer entry point: chunks of clouds pipelined over two streams, copies behind the kernels
+        from hitgeom.host import ChamferKnnHostStep
 
-    e2e_step()
+        host_step = ChamferKnnHostStep(N, chunk_clouds=min(128, B))
+        cloud_loss_h = np.empty(B, dtype=np.float32)
+
+        def e2e_step():
+            return host_step(adv_h, ori_h, grad_h, cloud_loss_out=cloud_loss_h)[0]
+
+    e2e_loss = e2e_step()
+    if args.workload != "c1":  # same kernels as the device-resident path: the gradient must be the same bits
+        assert torch.equal(grad_h, adv_d.grad.cpu()), "host-buffer step disagrees with the device-resident step"
     sharding.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
         l2_flush()
-        e2e_step()
+        e2e_loss = e2e_step()
     e1.record()
     torch.cuda.synchronize()
     sharding.barrier()
@@ -352,7 +364,10 @@ def main_hitgeom(args):
         "clocks": clocks, "roofline": roofline,
         "e2e": {"value": world * pairs_step / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": int(adv_h.numel() * 4 + ori_h.numel() * 4),
-                "d2h_bytes_per_step": int(grad_h.numel() * 4 + 4)},
+                "d2h_bytes_per_step": int(grad_h.numel() * 4 + (4 if args.workload == "c1" else 4 * B)),
+                "loss": e2e_loss,
+                "api": "torch module call + explicit copies" if args.workload == "c1" else
+                       "hg_chamfer_knn_step_host_f32 (C ABI, host buffers, 128-cloud chunks pipelined over two streams)"},
         "gpu_launches": int(launches),
     }
     if world == 1 and not args.no_cpu_baseline:

@@ -10,6 +10,7 @@ meaning and error behaviour), calling hand-written CUDA kernels through the C AB
                            query_ball_point, knn                  (model/pointnet2_utils.py, model/dgcnn_cls.py)
     hitgeom.pytorch3d_ops  knn_points, knn_gather                                      (pytorch3d.ops)
     hitgeom.install()      registers the above under the names the unmodified reference imports
+    hitgeom.host           ChamferKnnHostStep: the CW-kNN distance step on HOST buffers, chunk-pipelined over two streams
     hitgeom.sharding       instance-sharded multi-GPU driver (one process per GPU, NCCL all-gather at the end)
     hitgeom.hit_adv        HiT_ADV attacker with the fused deformation kernel and on-device bookkeeping
                            (ShapeAttack/HiT_ADV.py; SURVEY.md 8f "next" rows #1, #2)
@@ -33,6 +34,6 @@ def __getattr__(name):
     import importlib
 
     if name in ("set_distance", "dist_utils", "pointnet2_ops", "model_seams", "pytorch3d_ops", "functional",
-                "sharding", "hit_adv", "cw_knn", "clip_utils", "adv_utils", "eval_metrics"):
+                "sharding", "hit_adv", "cw_knn", "clip_utils", "adv_utils", "eval_metrics", "host"):
         return importlib.import_module(f".{name}", __name__)
     raise AttributeError(name)

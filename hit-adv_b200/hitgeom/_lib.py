@@ -45,6 +45,9 @@ _SIGNATURES = {
     "hg_index_points_grad_f32": (I, [P, P, I, I, I, I, P, P, Z, P]),
     "hg_hitadv_deform_fwd_f32": (I, [P, P, P, P, I, I, I, P, P, P]),
     "hg_hitadv_deform_bwd_f32": (I, [P, P, P, P, P, P, P, I, I, I, P, P, P]),
+    "hg_host_step_create": (P, [I, I, I]),
+    "hg_host_step_destroy": (None, [P]),
+    "hg_chamfer_knn_step_host_f32": (I, [P, P, P, I, I, I, F, F, F, P, P, P, P]),
     "hg_edge_feature_f32": (I, [P, P, I, I, I, I, P, P]),
     "hg_edge_feature_grad_workspace_bytes": (Z, [I, I, I]),
     "hg_edge_feature_grad_f32": (I, [P, P, I, I, I, I, P, P, Z, P]),

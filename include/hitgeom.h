@@ -187,6 +187,24 @@ size_t hg_edge_feature_grad_workspace_bytes(int B, int N, int k);
 int hg_edge_feature_grad_f32(const float *grad_out, const int64_t *idx, int B, int C, int N, int k, float *grad_x,
                              void *workspace, size_t workspace_bytes, hgStream stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * End-to-end entry point on HOST buffers: one CW-kNN distance step (CW/kNN.py:104-108 calling
+ * util/dist_utils.py:258-294 ChamferkNNDist(chamfer_method, knn_k, knn_alpha, chamfer_weight, knn_weight) with
+ * batch_avg=True) -- the exception to "every pointer is a device pointer": adv_h, ori_h [B,N,3], weights_h [B] or NULL,
+ * cloud_loss_h [B], grad_adv_h [B,N,3] and loss_h [1] are HOST pointers (page-locked memory lets the copies overlap).
+ *   cloud_loss[b] = w_b (chamfer_weight * chamfer_b + knn_weight * knn_b);  loss = mean_b cloud_loss[b];
+ *   grad_adv = d loss / d adv.   chamfer_method: 0 'adv2ori', 1 'ori2adv', 2 'both' (dist_utils.py:44-80).
+ * The batch is pipelined in chunks of `chunk_clouds` over two streams with their own device buffers (owned by the
+ * session), so host<->device copies hide behind the kernels; the call returns when loss and gradient are in place.
+ * A session serves any B and any knn_k <= knn_k_max for its N; it is bound to the device current at creation.
+ * ------------------------------------------------------------------------------------------------------- */
+typedef struct hgHostStep hgHostStep;
+hgHostStep *hg_host_step_create(int N, int chunk_clouds, int knn_k_max); /* NULL on failure (hg_last_error) */
+void hg_host_step_destroy(hgHostStep *session);
+int hg_chamfer_knn_step_host_f32(hgHostStep *session, const float *adv_h, const float *ori_h, int B, int chamfer_method,
+                                 int knn_k, float knn_alpha, float chamfer_weight, float knn_weight,
+                                 const float *weights_h, float *loss_h, float *cloud_loss_h, float *grad_adv_h);
+
 #ifdef __cplusplus
 }
 #endif
