@@ -171,7 +171,8 @@ HG_API int hg_chamfer_knn_step_host_f32(hgHostStep *s, const float *adv_h, const
                                                               chamfer_method, chamfer_weight, knn_weight, inv_b, sl.g1,
                                                               sl.g2, sl.gk, sl.total);
     HG_CHECK_LAUNCH("host_step_scales_kernel");
-    rc = hg_set_loss_bwd_f32(sl.ori, sl.adv, sl.arg1, sl.arg2, nullptr, nullptr, sl.g1, sl.g2, nb, N, N, 3,
+    rc = hg_set_loss_bwd_f32(sl.ori, sl.adv, sl.arg1, sl.arg2, nullptr, nullptr, chamfer_method == 1 ? nullptr : sl.g1,
+                             chamfer_method == 0 ? nullptr : sl.g2, nb, N, N, 3,
                              HG_MODE_CHAMFER, sl.grad_ch, nullptr, sl.ws, sl.ws_bytes, hs);
     if (rc) return rc;
     rc = hg_knn_outlier_bwd_f32(sl.adv, sl.idx, sl.mask, sl.gk, nb, N, 3, k1, sl.grad_knn, sl.ws, sl.ws_bytes, hs);

@@ -407,17 +407,20 @@ __global__ void __launch_bounds__(256) set_loss_bwd_kernel(
     const float *ps = self_pts + ((size_t)b * Ns + s) * D;
     const float *po = other_pts + (size_t)b * No * D;
     float cs, co;
+    // a null upstream = that loss is unused (ChamferDist's default 'adv2ori' never touches loss2): its term is
+    // skipped, and the host did not even build the reverse map (rev_off == nullptr)
+    const float gs = g_self ? g_self[b] : 0.f, go = g_other ? g_other[b] : 0.f;
     if (mode == HG_MODE_CHAMFER) {
-      cs = g_self[b] / (float)Ns;
-      co = g_other[b] / (float)No;
+      cs = gs / (float)Ns;
+      co = go / (float)No;
     } else {
-      cs = (hd_self[b] == s) ? g_self[b] : 0.f;
-      co = g_other[b];
+      cs = (hd_self[b] == s) ? gs : 0.f;
+      co = go;
     }
     const int a = self_arg[(size_t)b * Ns + s];
-    const int *off = rev_off + (size_t)b * (Ns + 1);
+    const int *off = rev_off ? rev_off + (size_t)b * (Ns + 1) : nullptr;
     const int *lst = rev_list + (size_t)b * No;
-    const int p0 = off[s], p1 = off[s + 1];
+    const int p0 = off ? off[s] : 0, p1 = off ? off[s + 1] : 0;
     const int hdo = (mode == HG_MODE_CHAMFER) ? -1 : hd_other[b];
     for (int c = chunk * cper; c < min(D, (chunk + 1) * cper); ++c) {
       const float v = ps[c];
@@ -573,7 +576,8 @@ HG_API int hg_set_loss_bwd_f32(const float *gts, const float *preds, const int *
                                int N1, int D, int mode, float *grad_preds, float *grad_gts, void *workspace,
                                size_t workspace_bytes, hgStream stream_) {
   cudaStream_t stream = hg_stream(stream_);
-  HG_REQUIRE(gts && preds && arg1 && arg2 && g1 && g2 && grad_preds, HG_E_BADARG, "set_loss_bwd: null pointer");
+  HG_REQUIRE(gts && preds && arg1 && arg2 && grad_preds, HG_E_BADARG, "set_loss_bwd: null pointer");
+  HG_REQUIRE(g1 || g2, HG_E_BADARG, "set_loss_bwd: g1 and g2 are both null (nothing to differentiate)");
   HG_REQUIRE(B > 0 && N1 > 0 && N2 > 0 && D > 0, HG_E_BADARG, "set_loss_bwd: sizes must be positive");
   HG_REQUIRE(mode == HG_MODE_CHAMFER || (mode == HG_MODE_HAUSDORFF && hd_arg1 && hd_arg2), HG_E_BADARG,
              "set_loss_bwd: bad mode / missing hausdorff arg-max indices");
@@ -581,8 +585,13 @@ HG_API int hg_set_loss_bwd_f32(const float *gts, const float *preds, const int *
              "set_loss_bwd: workspace too small");
   // preds (adv, "y"): gathers through arg1 (loss1), receives scatter from arg2 (loss2)
   HgCsr rev2;
-  int rc = hg_csr_build_unordered(arg2, B, N2, N1, workspace, hg_csr_workspace_bytes(B, N1, N2), &rev2, stream);
-  if (rc) return rc;
+  int rc = HG_OK;
+  rev2.off = nullptr;
+  rev2.list = nullptr;
+  if (g2) {  // loss2 scatters into preds through arg2; unused (g2 == NULL) => no reverse map at all
+    rc = hg_csr_build_unordered(arg2, B, N2, N1, workspace, hg_csr_workspace_bytes(B, N1, N2), &rev2, stream);
+    if (rc) return rc;
+  }
   const long long tp = (long long)B * N1 * (D > 8 ? D : 1);
   set_loss_bwd_kernel<<<grid_for(tp, 256), 256, 0, stream>>>(preds, gts, arg1, rev2.off, rev2.list, g1, g2, hd_arg1,
                                                              hd_arg2, B, N1, N2, D, mode, grad_preds);
@@ -590,8 +599,12 @@ HG_API int hg_set_loss_bwd_f32(const float *gts, const float *preds, const int *
   if (grad_gts) {
     HgCsr rev1;
     void *ws2 = (char *)workspace + hg_csr_workspace_bytes(B, N1, N2);
-    rc = hg_csr_build_unordered(arg1, B, N1, N2, ws2, hg_csr_workspace_bytes(B, N2, N1), &rev1, stream);
-    if (rc) return rc;
+    rev1.off = nullptr;
+    rev1.list = nullptr;
+    if (g1) {
+      rc = hg_csr_build_unordered(arg1, B, N1, N2, ws2, hg_csr_workspace_bytes(B, N2, N1), &rev1, stream);
+      if (rc) return rc;
+    }
     const long long tg = (long long)B * N2 * (D > 8 ? D : 1);
     set_loss_bwd_kernel<<<grid_for(tg, 256), 256, 0, stream>>>(gts, preds, arg2, rev1.off, rev1.list, g2, g1, hd_arg2,
                                                                hd_arg1, B, N2, N1, D, mode, grad_gts);

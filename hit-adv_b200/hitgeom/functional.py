@@ -82,6 +82,7 @@ class SetDistanceFn(torch.autograd.Function):
         loss1, loss2, hd1, hd2 = set_loss(min1, min2, mode)
         ctx.mode = mode
         ctx.saved = (preds_c, gts_c, arg1, arg2, hd1, hd2)
+        ctx.set_materialize_grads(False)  # an unused loss arrives as None, and its backward work is skipped
         return loss1, loss2
 
     @staticmethod
@@ -89,9 +90,11 @@ class SetDistanceFn(torch.autograd.Function):
         preds_c, gts_c, arg1, arg2, hd1, hd2 = ctx.saved
         B = preds_c.shape[0]
         dev = preds_c.device
-        g1 = torch.zeros(B, device=dev) if g1 is None else g1.to(torch.float32).contiguous()
-        g2 = torch.zeros(B, device=dev) if g2 is None else g2.to(torch.float32).contiguous()
         need_p, need_g = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        if g1 is None and g2 is None:
+            return (torch.zeros_like(preds_c) if need_p else None), (torch.zeros_like(gts_c) if need_g else None), None
+        g1 = None if g1 is None else g1.to(torch.float32).contiguous()
+        g2 = None if g2 is None else g2.to(torch.float32).contiguous()
         grad_preds, grad_gts = set_loss_bwd(gts_c, preds_c, arg1, arg2, hd1, hd2, g1, g2, ctx.mode, need_g)
         return (grad_preds if need_p else None), (grad_gts if need_g else None), None
 

@@ -77,8 +77,9 @@ int hg_set_loss_f32(const float *min1, const float *min2, int B, int N1, int N2,
                     float *loss2, int *hd_arg1, int *hd_arg2, hgStream stream);
 
 /* Backward of chamfer / hausdorff through the saved indices (what autograd derives for
- * set_distance.py:31,46-49,66-69).  g1/g2 [B] = dL/dloss1, dL/dloss2.  grad_preds [B,N1,D] is always
- * written; grad_gts [B,N2,D] may be NULL.  The scatter direction is a deterministic segmented sum. */
+ * set_distance.py:31,46-49,66-69).  g1/g2 [B] = dL/dloss1, dL/dloss2; either may be NULL = that loss is unused
+ * (ChamferDist's default 'adv2ori' never touches loss2): its term and its reverse map are skipped.  grad_preds
+ * [B,N1,D] is always written; grad_gts [B,N2,D] may be NULL.  The scatter direction is a deterministic segmented sum. */
 size_t hg_set_loss_bwd_workspace_bytes(int B, int N2, int N1);
 int hg_set_loss_bwd_f32(const float *gts, const float *preds, const int *arg1, const int *arg2, const int *hd_arg1,
                         const int *hd_arg2, const float *g1, const float *g2, int B, int N2, int N1, int D, int mode,
