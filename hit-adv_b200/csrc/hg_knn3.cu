@@ -24,11 +24,15 @@ namespace {
 
 constexpr int kThreads = 128;
 
+// internal third form (see filter_addend): EXPANDED values and indices, 4-operation folded filter
+#define HG_KNN_FORM_EXPANDED_FOLD4 2
+__host__ __device__ constexpr bool knn_form_expanded(int form) { return form != HG_KNN_FORM_DIRECT; }
+
 // exact scalar distance, identical operation sequence to the packed main loop
 template <int FORM>
 __device__ __forceinline__ float knn_dist_exact(float a0, float a1, float a2, float a3, float c0, float c1, float c2,
                                                 float cw) {
-  if (FORM == HG_KNN_FORM_EXPANDED) {  // a = (-2q0,-2q1,-2q2, xx_i), cw = xx_j
+  if (knn_form_expanded(FORM)) {  // a = (-2q0,-2q1,-2q2, xx_i), cw = xx_j
     const float nzz = __fmaf_rn(a2, c2, __fmaf_rn(a1, c1, __fmul_rn(a0, c0)));  // == -2*zz exactly
     return __fadd_rn(__fadd_rn(cw, nzz), a3);
   } else {  // a = (q0,q1,q2,-), c = NEGATED candidate: d = fma(dz,dz, fma(dy,dy, dx*dx)), dx = q0 + (-c0)
@@ -44,13 +48,24 @@ __device__ __forceinline__ float knn_dist_exact(float a0, float a1, float a2, fl
 // monotonicity of rounding: no candidate below the threshold is missed; the few extra flags (within one ulp of
 // the threshold) are rejected by the exact re-evaluation in the drain.  DIRECT: fl(d - thr) < 0 iff d < thr.
 // A +inf threshold gives af = -inf: every finite candidate is flagged; padding (s = +inf) gives NaN, sign clear.
+// Internal third form: EXPANDED arithmetic for everything that decides a value or an index, but a FOUR-operation
+// filter: e = fma(a0,c0, fma(a1,c1, fma(a2,c2, cw + af))), af = rd(a3 - T), T = thr + slack.  It is not the reference's
+// operation order, so it may differ from fl(s + a3) - thr by rounding: with u = 2^-24 and S = (|q| + max|c|)^2,
+//   |fl-chain(reference) - R| <= 8 u S   and   |e - (R - T)| <= 5 u (S + T)      (R = the exact real distance),
+// hence d < thr  =>  e < -slack + 8uS + 5u(S + T) < 0 once slack >= 24 u (S + thr) = 1.5e-6 (S + thr): nothing below
+// the threshold is missed; what the slack lets through extra (a relative 1e-6 band) dies in the exact drain.
+// Needs an upper bound on max|c|^2 per cloud (sbound); used on the seeded self-kNN path, where the grid pre-pass
+// has the bounding box anyway.
+
 template <int FORM>
-__device__ __forceinline__ float filter_addend(float a3, float thr) {
-  return FORM == HG_KNN_FORM_EXPANDED ? __fsub_rd(a3, thr) : -thr;
+__device__ __forceinline__ float filter_addend(float a3, float thr, float S) {
+  if (FORM == HG_KNN_FORM_EXPANDED) return __fsub_rd(a3, thr);
+  if (FORM == HG_KNN_FORM_EXPANDED_FOLD4) return __fsub_rd(a3, __fadd_ru(thr, 1.5e-6f * (S + thr)));
+  return -thr;
 }
 
-// packed filter value of one candidate pair (A = (c0_j, c0_j1, c1_j, c1_j1), B = (c2_j, c2_j1, w_j, w_j1)): same
-// operation sequence as knn_dist_exact except that the last addend carries the threshold
+// packed filter value of one candidate pair (A = (c0_j, c0_j1, c1_j, c1_j1), B = (c2_j, c2_j1, w_j, w_j1)).
+// EXPANDED / DIRECT: same operation sequence as knn_dist_exact except that the last addend carries the threshold.
 template <int FORM>
 __device__ __forceinline__ float2 filter_value(float a0, float a1, float a2, float af, float4 cA, float4 cB) {
   if (FORM == HG_KNN_FORM_EXPANDED) {
@@ -59,6 +74,11 @@ __device__ __forceinline__ float2 filter_value(float a0, float a1, float a2, flo
     tt = __ffma2_rn(make_float2(a2, a2), make_float2(cB.x, cB.y), tt);
     const float2 s = __fadd2_rn(make_float2(cB.z, cB.w), tt);
     return __fadd2_rn(s, make_float2(af, af));
+  } else if (FORM == HG_KNN_FORM_EXPANDED_FOLD4) {
+    float2 tt = __fadd2_rn(make_float2(cB.z, cB.w), make_float2(af, af));
+    tt = __ffma2_rn(make_float2(a2, a2), make_float2(cB.x, cB.y), tt);
+    tt = __ffma2_rn(make_float2(a1, a1), make_float2(cA.z, cA.w), tt);
+    return __ffma2_rn(make_float2(a0, a0), make_float2(cA.x, cA.y), tt);
   } else {
     const float2 dx = __fadd2_rn(make_float2(a0, a0), make_float2(cA.x, cA.y));
     const float2 dy = __fadd2_rn(make_float2(a1, a1), make_float2(cA.z, cA.w));
@@ -107,7 +127,9 @@ template <int FORM, int QT, int KM, int GP, typename IdxT>
 __global__ void __launch_bounds__(kThreads) knn3_kernel(const float *__restrict__ queries,
                                                         const float *__restrict__ refs, int Nq, int Nr, int k1,
                                                         float *__restrict__ vals, IdxT *__restrict__ idx,
-                                                        const float *__restrict__ thr0 /*[B,Nq] or null*/) {
+                                                        const float *__restrict__ thr0 /*[B,Nq] or null*/,
+                                                        const float *__restrict__ sbound /*FOLD4: [B] stride 8,
+                                                        upper bound on max |candidate|^2*/) {
   constexpr int kTilePairs = 32 * GP;
   constexpr int kTileC = 2 * kTilePairs;
   __shared__ float4 cand[2 * kTilePairs];  // two float4 per candidate pair
@@ -115,7 +137,8 @@ __global__ void __launch_bounds__(kThreads) knn3_kernel(const float *__restrict_
   const float *q = queries + (size_t)b * Nq * 3;
   const float *r = refs + (size_t)b * Nr * 3;
 
-  float a0[QT], a1[QT], a2[QT], a3[QT], af[QT], seed[QT];
+  float a0[QT], a1[QT], a2[QT], a3[QT], af[QT], seed[QT], S[QT];
+  const float cmax = (FORM == HG_KNN_FORM_EXPANDED_FOLD4) ? sqrtf(sbound[(size_t)b * 8]) : 0.f;
   unsigned mask[QT];
   TopK<KM> top[QT];
 #pragma unroll
@@ -127,7 +150,7 @@ __global__ void __launch_bounds__(kThreads) knn3_kernel(const float *__restrict_
       q1 = __ldg(q + (size_t)i * 3 + 1);
       q2 = __ldg(q + (size_t)i * 3 + 2);
     }
-    if (FORM == HG_KNN_FORM_EXPANDED) {
+    if (knn_form_expanded(FORM)) {
       a0[t] = -2.0f * q0;
       a1[t] = -2.0f * q1;
       a2[t] = -2.0f * q2;
@@ -141,7 +164,8 @@ __global__ void __launch_bounds__(kThreads) knn3_kernel(const float *__restrict_
     // optional upper bound on this query's KM-th distance (knn_seed_kernel): the filter starts tight instead of
     // at +inf, so only ~KM candidates ever reach the drain instead of ~KM ln(N/KM)
     seed[t] = (thr0 != nullptr && i < Nq) ? thr0[(size_t)b * Nq + i] : CUDART_INF_F;
-    af[t] = filter_addend<FORM>(a3[t], seed[t]);
+    S[t] = (sqrtf(a3[t]) + cmax) * (sqrtf(a3[t]) + cmax) * 1.0001f;
+    af[t] = filter_addend<FORM>(a3[t], seed[t], S[t]);
     mask[t] = 0u;
     top[t].init();
   }
@@ -158,14 +182,14 @@ __global__ void __launch_bounds__(kThreads) knn3_kernel(const float *__restrict_
         c[h][3] = CUDART_INF_F;  // padding can never beat a threshold (EXPANDED: inf; DIRECT: handled below)
         if (j < Nr) {
           const float x = __ldg(r + (size_t)j * 3), y = __ldg(r + (size_t)j * 3 + 1), z = __ldg(r + (size_t)j * 3 + 2);
-          if (FORM == HG_KNN_FORM_EXPANDED) {
+          if (knn_form_expanded(FORM)) {
             c[h][0] = x; c[h][1] = y; c[h][2] = z;
             c[h][3] = hg_sumsq3_seq(x, y, z);
           } else {
             c[h][0] = -x; c[h][1] = -y; c[h][2] = -z;
             c[h][3] = 0.f;
           }
-        } else if (FORM != HG_KNN_FORM_EXPANDED) {
+        } else if (!knn_form_expanded(FORM)) {
           c[h][0] = CUDART_INF_F;  // dx = q + inf = inf -> d = inf
         }
       }
@@ -236,7 +260,7 @@ __global__ void __launch_bounds__(kThreads) knn3_kernel(const float *__restrict_
           }
         }
         mask[t] = 0u;
-        af[t] = filter_addend<FORM>(a3[t], fminf(seed[t], top[t].v[KM - 1]));
+        af[t] = filter_addend<FORM>(a3[t], fminf(seed[t], top[t].v[KM - 1]), S[t]);
       }
       g0 += cnt;
       if (base == 0 && step < 8 && g0 >= 2 * step) step *= 2;  // 1,1,2,4,8,8,8
@@ -260,15 +284,15 @@ __global__ void __launch_bounds__(kThreads) knn3_kernel(const float *__restrict_
 
 template <int FORM, int QT, int KM, typename IdxT>
 int launch_qt(const float *q, const float *r, int B, int Nq, int Nr, int k1, float *vals, IdxT *idx,
-              const float *thr0, cudaStream_t stream) {
+              const float *thr0, const float *sbound, cudaStream_t stream) {
   dim3 grid((Nq + QT * kThreads - 1) / (QT * kThreads), B);
   const bool prof = hg_prof_begin(HG_PROF_KNN, stream);
   // 8 candidates per hit bit (512-candidate tiles) for long candidate lists, 4 (256) for short ones, where the
   // cheaper group re-evaluation in the drain outweighs the extra mask updates (measured cross-over ~2-4k)
   if (Nr < 2048)
-    knn3_kernel<FORM, QT, KM, 2, IdxT><<<grid, kThreads, 0, stream>>>(q, r, Nq, Nr, k1, vals, idx, thr0);
+    knn3_kernel<FORM, QT, KM, 2, IdxT><<<grid, kThreads, 0, stream>>>(q, r, Nq, Nr, k1, vals, idx, thr0, sbound);
   else
-    knn3_kernel<FORM, QT, KM, 4, IdxT><<<grid, kThreads, 0, stream>>>(q, r, Nq, Nr, k1, vals, idx, thr0);
+    knn3_kernel<FORM, QT, KM, 4, IdxT><<<grid, kThreads, 0, stream>>>(q, r, Nq, Nr, k1, vals, idx, thr0, sbound);
   hg_prof_end(HG_PROF_KNN, stream, prof);
   HG_CHECK_LAUNCH("knn3_kernel");
   return HG_OK;
@@ -276,7 +300,7 @@ int launch_qt(const float *q, const float *r, int B, int Nq, int Nr, int k1, flo
 
 template <int FORM, typename IdxT>
 int launch_form(const float *q, const float *r, int B, int Nq, int Nr, int k1, float *vals, IdxT *idx,
-                const float *thr0, cudaStream_t stream) {
+                const float *thr0, const float *sbound, cudaStream_t stream) {
   if (k1 < 1 || k1 > 32) {
     hg_set_error("knn: k=%d outside [1,32]", k1);
     return HG_E_UNSUPPORTED;
@@ -284,15 +308,15 @@ int launch_form(const float *q, const float *r, int B, int Nq, int Nr, int k1, f
   // queries per lane: amortise the candidate loads, but keep small query sets spread over the machine and the
   // register-resident lists (2*KM registers per query) within budget
   if (k1 <= 6) {
-    if (Nq >= 3 * kThreads) return launch_qt<FORM, 4, 6, IdxT>(q, r, B, Nq, Nr, k1, vals, idx, thr0, stream);
-    if (Nq > kThreads) return launch_qt<FORM, 2, 6, IdxT>(q, r, B, Nq, Nr, k1, vals, idx, thr0, stream);
-    return launch_qt<FORM, 1, 6, IdxT>(q, r, B, Nq, Nr, k1, vals, idx, thr0, stream);
+    if (Nq >= 3 * kThreads) return launch_qt<FORM, 4, 6, IdxT>(q, r, B, Nq, Nr, k1, vals, idx, thr0, sbound, stream);
+    if (Nq > kThreads) return launch_qt<FORM, 2, 6, IdxT>(q, r, B, Nq, Nr, k1, vals, idx, thr0, sbound, stream);
+    return launch_qt<FORM, 1, 6, IdxT>(q, r, B, Nq, Nr, k1, vals, idx, thr0, sbound, stream);
   }
   if (k1 <= 20) {
-    if (Nq > kThreads) return launch_qt<FORM, 2, 20, IdxT>(q, r, B, Nq, Nr, k1, vals, idx, thr0, stream);
-    return launch_qt<FORM, 1, 20, IdxT>(q, r, B, Nq, Nr, k1, vals, idx, thr0, stream);
+    if (Nq > kThreads) return launch_qt<FORM, 2, 20, IdxT>(q, r, B, Nq, Nr, k1, vals, idx, thr0, sbound, stream);
+    return launch_qt<FORM, 1, 20, IdxT>(q, r, B, Nq, Nr, k1, vals, idx, thr0, sbound, stream);
   }
-  return launch_qt<FORM, 1, 32, IdxT>(q, r, B, Nq, Nr, k1, vals, idx, thr0, stream);
+  return launch_qt<FORM, 1, 32, IdxT>(q, r, B, Nq, Nr, k1, vals, idx, thr0, sbound, stream);
 }
 
 // ---- threshold seeding for self-kNN ---------------------------------------------------------------------------
@@ -342,6 +366,12 @@ __global__ void __launch_bounds__(256) knn_cells_kernel(const float *__restrict_
   if (tid < 3) {
     params[b * 8 + tid] = mn[tid];
     params[b * 8 + 3 + tid] = inv[tid];
+  }
+  if (tid == 0) {  // upper bound on max |p|^2 over the cloud (the farthest bounding-box corner), for the folded filter
+    float sb = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) sb += fmaxf(red[c][0] * red[c][0], red[3 + c][0] * red[3 + c][0]);
+    params[b * 8 + 6] = sb * 1.0001f;
   }
   for (int i = tid; i < N; i += 256) {
     int cc[3];
@@ -427,15 +457,15 @@ int seed_grid(int N) {
 int hg_knn3_launch_i32(int form, const float *q, const float *r, int B, int Nq, int Nr, int k1, float *vals, int *idx,
                        cudaStream_t stream) {
   return form == HG_KNN_FORM_EXPANDED
-             ? launch_form<HG_KNN_FORM_EXPANDED, int>(q, r, B, Nq, Nr, k1, vals, idx, nullptr, stream)
-             : launch_form<HG_KNN_FORM_DIRECT, int>(q, r, B, Nq, Nr, k1, vals, idx, nullptr, stream);
+             ? launch_form<HG_KNN_FORM_EXPANDED, int>(q, r, B, Nq, Nr, k1, vals, idx, nullptr, nullptr, stream)
+             : launch_form<HG_KNN_FORM_DIRECT, int>(q, r, B, Nq, Nr, k1, vals, idx, nullptr, nullptr, stream);
 }
 
 int hg_knn3_launch_i64(int form, const float *q, const float *r, int B, int Nq, int Nr, int k1, float *vals,
                        long long *idx, cudaStream_t stream) {
   return form == HG_KNN_FORM_EXPANDED
-             ? launch_form<HG_KNN_FORM_EXPANDED, long long>(q, r, B, Nq, Nr, k1, vals, idx, nullptr, stream)
-             : launch_form<HG_KNN_FORM_DIRECT, long long>(q, r, B, Nq, Nr, k1, vals, idx, nullptr, stream);
+             ? launch_form<HG_KNN_FORM_EXPANDED, long long>(q, r, B, Nq, Nr, k1, vals, idx, nullptr, nullptr, stream)
+             : launch_form<HG_KNN_FORM_DIRECT, long long>(q, r, B, Nq, Nr, k1, vals, idx, nullptr, nullptr, stream);
 }
 
 size_t hg_knn3_seed_workspace_bytes(int B, int N) {
@@ -449,7 +479,7 @@ size_t hg_knn3_seed_workspace_bytes(int B, int N) {
 int hg_knn3_self_seeded_i32(const float *pc, int B, int N, int k1, float *vals, int *idx, void *workspace,
                             size_t workspace_bytes, cudaStream_t stream) {
   if (N < 512 || k1 > 32 || workspace == nullptr || workspace_bytes < hg_knn3_seed_workspace_bytes(B, N))
-    return launch_form<HG_KNN_FORM_EXPANDED, int>(pc, pc, B, N, N, k1, vals, idx, nullptr, stream);
+    return launch_form<HG_KNN_FORM_EXPANDED, int>(pc, pc, B, N, N, k1, vals, idx, nullptr, nullptr, stream);
   const int G = seed_grid(N), ncell = G * G * G;
   char *w = (char *)workspace;
   int *cellid = (int *)w;
@@ -481,5 +511,6 @@ int hg_knn3_self_seeded_i32(const float *pc, int B, int N, int k1, float *vals, 
   else
     knn_seed_kernel<32><<<grid, 128, 0, stream>>>(sorted, N, G, params, csr.off, csr.list, thr0);
   HG_CHECK_LAUNCH("knn_seed_kernel");
-  return launch_form<HG_KNN_FORM_EXPANDED, int>(pc, pc, B, N, N, k1, vals, idx, thr0, stream);
+  // seeded path: the bounding box is known, so the main loop can run the 4-operation folded filter
+  return launch_form<HG_KNN_FORM_EXPANDED_FOLD4, int>(pc, pc, B, N, N, k1, vals, idx, thr0, params + 6, stream);
 }

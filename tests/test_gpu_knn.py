@@ -129,3 +129,19 @@ def test_knn_seeded_and_unseeded_agree(oracle, F):
     flat = np.zeros((1, 2048, 3), np.float32)  # every point identical: one cell, all distances equal
     vals, idx = F.knn_self(gpu(flat), 6)
     assert np.array_equal(idx.cpu().numpy()[0], np.tile(np.arange(6, dtype=np.int32), (2048, 1)))
+
+
+@pytest.mark.parametrize("k1", [6, 20])
+def test_knn_folded_filter_is_conservative_far_from_origin(oracle, F, k1):
+    """The seeded path filters with a 4-operation folded form whose rounding differs from the reference's; its slack
+    is sized from (|q| + max|c|)^2.  A small cloud far from the origin is the worst case: the expanded-form distances
+    are cancellation noise (norms ~ 1e4, spacings ~ 1e-2), many candidates tie or sit within the slack band -- values
+    and indices must still be the oracle's, bit for bit."""
+    rng = np.random.default_rng(k1)
+    for offset, scale in (((60.0, -35.0, 20.0), 0.05), ((0.5, 0.5, 0.5), 1.0), ((1000.0, 0.0, 0.0), 1.0)):
+        pc = (clouds(2, 2048, 91, "gauss") * scale + np.asarray(offset, np.float32)).astype(np.float32)
+        pc[1, :64] = pc[1, 64:128]  # duplicates
+        pc[0] = pc[0][rng.permutation(2048)]
+        vals, idx = F.knn_self(gpu(pc), k1)
+        ov, oi = oracle.knn_self(pc, k1, threads=4)
+        assert np.array_equal(vals.cpu().numpy(), ov) and np.array_equal(idx.cpu().numpy(), oi), (offset, scale)
