@@ -10,6 +10,7 @@ import torch
 import torch.nn as nn
 
 from . import functional as F
+from .functional import shared_distance_pass  # noqa: F401  (opt-in: Chamfer + Hausdorff of one pair share a pass)
 from .set_distance import chamfer, hausdorff
 
 

@@ -71,6 +71,39 @@ def set_loss_bwd(gts, preds, arg1, arg2, hd1, hd2, g1, g2, mode, want_gts):
     return grad_preds, grad_gts
 
 
+class shared_distance_pass:
+    """`with shared_distance_pass(): loss = chamfer(adv, ori) + hausdorff(adv, ori)` -- inside the block, Chamfer and
+    Hausdorff losses of the SAME pair of tensors share one distance pass (the reference builds P twice,
+    set_distance.py:44,61; SURVEY.md 8d counts one).  Sharing is keyed on tensor identity + version and is only active
+    inside the block: the caller asserts that the clouds are not modified through `.data` between the two calls."""
+    _depth = 0
+    _entries = []
+
+    def __enter__(self):
+        shared_distance_pass._depth += 1
+        return self
+
+    def __exit__(self, *exc):
+        shared_distance_pass._depth -= 1
+        if shared_distance_pass._depth == 0:
+            shared_distance_pass._entries.clear()
+        return False
+
+    @staticmethod
+    def lookup(preds, gts, preds_c, gts_c):
+        if shared_distance_pass._depth == 0:
+            return nn_bidir(gts_c, preds_c)
+        key = (preds_c.data_ptr(), preds._version, gts_c.data_ptr(), gts._version, tuple(preds_c.shape),
+               tuple(gts_c.shape), stream_ptr())
+        for k, _, res in shared_distance_pass._entries:
+            if k == key:
+                return res
+        res = nn_bidir(gts_c, preds_c)
+        # the entry keeps its inputs alive, so their addresses cannot be recycled for other tensors meanwhile
+        shared_distance_pass._entries.append((key, (preds, gts, preds_c, gts_c), res))
+        return res
+
+
 class SetDistanceFn(torch.autograd.Function):
     """(preds, gts) -> (loss1 [B], loss2 [B]) for Chamfer (mode 0) / Hausdorff (mode 1)."""
 
@@ -78,7 +111,7 @@ class SetDistanceFn(torch.autograd.Function):
     def forward(ctx, preds, gts, mode):
         preds_c = preds.detach().contiguous()
         gts_c = gts.detach().contiguous()
-        min1, arg1, min2, arg2 = nn_bidir(gts_c, preds_c)
+        min1, arg1, min2, arg2 = shared_distance_pass.lookup(preds, gts, preds_c, gts_c)
         loss1, loss2, hd1, hd2 = set_loss(min1, min2, mode)
         ctx.mode = mode
         ctx.saved = (preds_c, gts_c, arg1, arg2, hd1, hd2)

@@ -178,3 +178,38 @@ def test_errors_are_exceptions(F):
         F.nn_bidir(torch.zeros(1, 4, 3, device="cuda", dtype=torch.float64), torch.zeros(1, 4, 3, device="cuda"))
     with pytest.raises((HitgeomError, RuntimeError)):
         F.knn_self(torch.zeros(1, 4, 3, device="cuda"), 9)  # k > K
+
+
+def test_shared_distance_pass_is_transparent():
+    """Inside `shared_distance_pass()` Chamfer + Hausdorff of the same pair run ONE distance pass; values and gradients
+    are the bits of the unshared computation, and a modified cloud (version bump) is never served from the cache."""
+    from hitgeom import _lib
+    from hitgeom.dist_utils import ChamferDist, HausdorffDist, shared_distance_pass
+
+    ori = gpu(clouds(4, 700, 3))
+    adv = gpu(jitter(clouds(4, 700, 3), 8)).requires_grad_()
+    cd, hd = ChamferDist(method="ori2adv"), HausdorffDist(method="adv2ori")
+
+    def run(shared):
+        adv.grad = None
+        n0 = _lib.launch_count()
+        if shared:
+            with shared_distance_pass():
+                loss = cd(adv, ori) + hd(adv, ori)
+        else:
+            loss = cd(adv, ori) + hd(adv, ori)
+        launches = _lib.launch_count() - n0
+        loss.backward()
+        return loss.detach().clone(), adv.grad.clone(), launches
+
+    l0, g0, n_plain = run(False)
+    l1, g1, n_shared = run(True)
+    assert torch.equal(l0, l1) and torch.equal(g0, g1)
+    assert n_shared < n_plain
+    with shared_distance_pass():
+        a = cd(adv, ori)
+        with torch.no_grad():
+            adv.add_(0.01)  # in-place update (what an optimiser step does): bumps the version
+        b = cd(adv, ori)
+        assert a.item() != b.item()
+    assert torch.equal(b.detach(), cd(adv, ori).detach())
