@@ -445,6 +445,25 @@ __global__ void __launch_bounds__(128) knn_seed_kernel(const float4 *__restrict_
   thr0[(size_t)b * N + list[(size_t)b * N + s_q]] = (bound < CUDART_INF_F) ? nextafterf(bound, CUDART_INF_F) : CUDART_INF_F;
 }
 
+// upper bound on max |p|^2 per cloud for the folded filter when no grid pre-pass runs: sbound[b*8] (stride 8, like params+6)
+__global__ void __launch_bounds__(256) knn_bound_kernel(const float *__restrict__ pc, int N, float *__restrict__ sbound) {
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const float *p = pc + (size_t)b * N * 3;
+  float m = 0.f;
+  for (int i = tid; i < N; i += 256) {
+    const float x = p[(size_t)i * 3], y = p[(size_t)i * 3 + 1], z = p[(size_t)i * 3 + 2];
+    m = fmaxf(m, fmaf(z, z, fmaf(y, y, x * x)));
+  }
+  m = hg_warp_max_f32(m);
+  __shared__ float red[8];
+  if ((tid & 31) == 0) red[tid >> 5] = m;
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w]);
+    sbound[(size_t)b * 8] = m * 1.0001f;
+  }
+}
+
 int seed_grid(int N) {
   int G = (int)lroundf(cbrtf((float)N / 3.0f));
   if (G < 1) G = 1;
@@ -475,11 +494,23 @@ size_t hg_knn3_seed_workspace_bytes(int B, int N) {
          hg_csr_workspace_bytes(B, G * G * G, N);
 }
 
+// Benchmark-only override of the smallest cloud that gets grid-seeded thresholds (0 = default).
+static int g_seed_min_n = 0;
+HG_API void hg_knn_tune(int seed_min_n) { g_seed_min_n = seed_min_n; }
+
 // self-kNN (expanded form) with grid-seeded thresholds; falls back to the unseeded launch for small clouds
 int hg_knn3_self_seeded_i32(const float *pc, int B, int N, int k1, float *vals, int *idx, void *workspace,
                             size_t workspace_bytes, cudaStream_t stream) {
-  if (N < 512 || k1 > 32 || workspace == nullptr || workspace_bytes < hg_knn3_seed_workspace_bytes(B, N))
+  if (k1 > 32 || workspace == nullptr || workspace_bytes < hg_knn3_seed_workspace_bytes(B, N))
     return launch_form<HG_KNN_FORM_EXPANDED, int>(pc, pc, B, N, N, k1, vals, idx, nullptr, nullptr, stream);
+  if (N < (g_seed_min_n > 0 ? g_seed_min_n : 2048)) {
+    // small clouds: cold thresholds (the grid pre-pass costs more than the insertions it saves, measured below
+    // ~2k points), but still the 4-operation folded filter -- it only needs a bound on max |p|^2
+    float *sb = (float *)((char *)workspace + hg_align((size_t)B * N * sizeof(int)));  // the `params` slot
+    knn_bound_kernel<<<B, 256, 0, stream>>>(pc, N, sb);
+    HG_CHECK_LAUNCH("knn_bound_kernel");
+    return launch_form<HG_KNN_FORM_EXPANDED_FOLD4, int>(pc, pc, B, N, N, k1, vals, idx, nullptr, sb, stream);
+  }
   const int G = seed_grid(N), ncell = G * G * G;
   char *w = (char *)workspace;
   int *cellid = (int *)w;
