@@ -390,9 +390,13 @@ def main_hitgeom(args):
     k_avg_ms = k_ms / max(k_n, 1)
     achieved = k_pairs * FLOP_PER_PAIR / (k_avg_ms * 1e-3) / 1e12 if k_avg_ms > 0 else 0.0
     alg_bytes = B * (2 * N) * 12 + B * (2 * N) * 8
+    # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch at the default workload's size, from `ncu --set full`
+    # captures (profiles/r01_ncu_full_nn_1024clouds.txt, r01_ncu_full_knn_1024clouds.txt); other sizes: not captured
+    ncu_traffic = {"nn_bidir_d3_kernel": 919.4e6, "knn3_kernel": 1026.3e6} if (B, N, args.workload) == (1024, 16384, "c5shard") else {}
     roofline = {
         "bound": "fp32", "kernel": kname, "achieved": achieved, "peak": fp32_peak_tflops, "unit": "TFLOP/s",
-        "frac": achieved / fp32_peak_tflops if fp32_peak_tflops else None, "traffic": None,
+        "frac": achieved / fp32_peak_tflops if fp32_peak_tflops else None, "traffic": ncu_traffic.get(kname),
+        "traffic_source": "ncu --set full, one launch at this size (profiles/r01_ncu_full_*_1024clouds.txt)" if kname in ncu_traffic else None,
         "peak_source": f"computed {info['sm_count']} SMs x 128 FP32 lanes x 2 x {sm_max_mhz:.0f} MHz (no FP32 figure in MEASURED_PEAKS.json)",
         "avg_launch_ms": k_avg_ms, "launches_timed": k_n, "algorithmic_pair_evals_per_launch": k_pairs,
         "flop_per_pair_eval": FLOP_PER_PAIR,
