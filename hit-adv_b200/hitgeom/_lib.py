@@ -24,7 +24,7 @@ _SIGNATURES = {
     "hg_nn_bidir_workspace_bytes": (Z, [I, I, I, I]),
     "hg_nn_bidir_f32": (I, [P, P, I, I, I, I, P, P, P, P, P, Z, P]),
     "hg_nn_bidir_tune": (None, [I, I]),
-    "hg_knn_tune": (None, [I]),
+    "hg_knn_tune": (None, [I, I]),
     "hg_launch_count": (ctypes.c_ulonglong, []),
     "hg_prof_enable": (None, [I]),
     "hg_prof_read": (I, [I, ctypes.POINTER(F), ctypes.POINTER(I)]),

@@ -54,8 +54,9 @@ void hg_prof_enable(int on);
 int hg_prof_read(int tag, float *total_ms, int *launches);
 /* Benchmark-only override of the nn_bidir tile shape: T = columns per lane (8 or 16), RB = rows per CTA; 0 = auto. */
 void hg_nn_bidir_tune(int T, int RB);
-/* Benchmark-only override: smallest cloud size whose self-kNN gets grid-seeded thresholds (0 = default). */
-void hg_knn_tune(int seed_min_n);
+/* Benchmark-only overrides: smallest cloud size whose self-kNN gets grid-seeded thresholds (0 = default), and the
+ * seed scan's cell neighbourhood (0 = automatic, 1 = 2x2x2, 2 = 3x3x3). */
+void hg_knn_tune(int seed_min_n, int neighbourhood);
 
 /* ---------------------------------------------------------------------------------------------------------
  * util/set_distance.py:15-32,45-48,65-68 -- `_Distance.batch_pairwise_dist` fused with the two `torch.min`

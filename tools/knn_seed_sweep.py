@@ -31,8 +31,9 @@ for N in (512, 1024, 2048, 4096, 8192, 16384):
     x = x / x.norm(dim=-1).amax(dim=1)[:, None, None]
     for k1 in (6, 20):
         res = {}
-        for name, minn in (("seeded", 1), ("unseeded", 1 << 30)):
-            _lib.lib().hg_knn_tune(minn)
+        for name, minn, near8 in (("seeded27", 1, 2), ("seeded8", 1, 1), ("unseeded", 1 << 30, 0)):
+            _lib.lib().hg_knn_tune(minn, near8)
             res[name] = timed(lambda: F.knn_self(x, k1))
-        print(f"B={B} N={N} k1={k1}: seeded {res['seeded']:.3f} ms  unseeded {res['unseeded']:.3f} ms  ratio {res['unseeded'] / res['seeded']:.2f}", flush=True)
-_lib.lib().hg_knn_tune(0)
+        print(f"B={B} N={N} k1={k1}: seeded(27 cells) {res['seeded27']:.3f} ms  seeded(8 cells) {res['seeded8']:.3f} ms  "
+              f"unseeded {res['unseeded']:.3f} ms", flush=True)
+_lib.lib().hg_knn_tune(0, 0)
