@@ -35,6 +35,64 @@ __device__ __forceinline__ float sumsq_cascade(const float *a, int C) {
   return __fadd_rn(__fadd_rn(acc0, acc1), acc2);
 }
 
+// A CTA owns (b, 32 source rows, 1024 target columns): every thread keeps its four target points (and their squared
+// norms) in registers and walks the 32 source rows staged in shared memory -- one float4 store per row, no integer
+// division, each input read once per CTA; HBM-bound on the [B,N,M] output.  C <= 8 (the model calls it with C = 3);
+// wider features take the generic kernel below.
+constexpr int kSqRows = 32, kSqMaxC = 8;
+__global__ void __launch_bounds__(256) square_distance_small_c_kernel(const float *__restrict__ src,
+                                                                      const float *__restrict__ dst, int N, int M,
+                                                                      int C, float *__restrict__ out) {
+  __shared__ float srow[kSqRows][kSqMaxC + 1];  // [row][c], last = squared norm
+  const int b = blockIdx.z, n0 = blockIdx.y * kSqRows;
+  for (int t = threadIdx.x; t < kSqRows; t += 256) {
+    const int n = n0 + t;
+    if (n < N) {
+      const float *sp = src + ((size_t)b * N + n) * C;
+      for (int c = 0; c < C; ++c) srow[t][c] = sp[c];
+      srow[t][kSqMaxC] = sumsq_cascade(sp, C);
+    }
+  }
+  const int m0 = (blockIdx.x * 256 + threadIdx.x) * 4;
+  float d[4][kSqMaxC], rd[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    rd[u] = 0.f;
+#pragma unroll
+    for (int c = 0; c < kSqMaxC; ++c) d[u][c] = 0.f;
+    if (m0 + u < M) {
+      const float *dp = dst + ((size_t)b * M + m0 + u) * C;
+#pragma unroll
+      for (int c = 0; c < kSqMaxC; ++c)
+        if (c < C) d[u][c] = dp[c];
+      rd[u] = sumsq_cascade(dp, C);
+    }
+  }
+  __syncthreads();
+  if (m0 >= M) return;
+  const bool vec = (M & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+  const int rows = min(kSqRows, N - n0);
+  for (int t = 0; t < rows; ++t) {
+    float v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float zz = __fmul_rn(srow[t][0], d[u][0]);
+#pragma unroll
+      for (int c = 1; c < kSqMaxC; ++c)
+        if (c < C) zz = __fmaf_rn(srow[t][c], d[u][c], zz);
+      v[u] = __fadd_rn(__fadd_rn(__fmul_rn(-2.0f, zz), srow[t][kSqMaxC]), rd[u]);
+    }
+    float *o = out + ((size_t)b * N + n0 + t) * M + m0;
+    if (vec) {
+      __stcs(reinterpret_cast<float4 *>(o), make_float4(v[0], v[1], v[2], v[3]));
+    } else {
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (m0 + u < M) o[u] = v[u];
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) square_distance_kernel(const float *__restrict__ src,
                                                               const float *__restrict__ dst, int B, int N, int M,
                                                               int C, float *__restrict__ out) {
@@ -134,8 +192,13 @@ HG_API int hg_square_distance_f32(const float *src, const float *dst, int B, int
                                   hgStream stream_) {
   HG_REQUIRE(src && dst && out, HG_E_BADARG, "square_distance: null pointer");
   HG_REQUIRE(B > 0 && N > 0 && M > 0 && C > 0, HG_E_BADARG, "square_distance: sizes must be positive");
-  const long long total = (long long)B * N * M;
-  square_distance_kernel<<<grid_for(total, 256), 256, 0, hg_stream(stream_)>>>(src, dst, B, N, M, C, out);
+  if (C <= kSqMaxC && B <= 65535 && (N + kSqRows - 1) / kSqRows <= 65535) {
+    dim3 grid((M + 1023) / 1024, (N + kSqRows - 1) / kSqRows, B);
+    square_distance_small_c_kernel<<<grid, 256, 0, hg_stream(stream_)>>>(src, dst, N, M, C, out);
+  } else {
+    const long long total = (long long)B * N * M;
+    square_distance_kernel<<<grid_for(total, 256), 256, 0, hg_stream(stream_)>>>(src, dst, B, N, M, C, out);
+  }
   HG_CHECK_LAUNCH("square_distance");
   return HG_OK;
 }

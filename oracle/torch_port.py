@@ -101,3 +101,50 @@ def get_graph_feature(x, idx):
     feature = xt.view(B * N, -1)[flat, :].view(B, N, k, C)
     xr = xt.view(B, N, 1, C).repeat(1, 1, k, 1)
     return torch.cat((feature - xr, xr), dim=3).permute(0, 3, 1, 2).contiguous()
+
+
+# ---- the PointNet++ SSG victim's torch-level geometry (model/pointnet2_utils.py:19-107), same tensor programs ---------
+def square_distance(src, dst):
+    """:19-40  -2 src.dst^T, then += |src|^2, then += |dst|^2 (in place, in this order)."""
+    d = -2 * torch.matmul(src, dst.permute(0, 2, 1))
+    d += torch.sum(src ** 2, -1).unsqueeze(2)
+    d += torch.sum(dst ** 2, -1).unsqueeze(1)
+    return d
+
+
+def index_points(points, idx):
+    """:43-60  batched advanced-index gather."""
+    B = points.shape[0]
+    shape = [B] + [1] * (idx.dim() - 1)
+    batch = torch.arange(B, dtype=torch.long, device=points.device).view(shape).expand_as(idx)
+    return points[batch, idx, :]
+
+
+def farthest_point_sample(xyz, npoint, start):
+    """:63-84 with the `torch.randint` start handed in: npoint rounds of gather, squared distance, masked min, argmax."""
+    B, N, _ = xyz.shape
+    centroids = torch.zeros(B, npoint, dtype=torch.long, device=xyz.device)
+    distance = torch.ones(B, N, device=xyz.device) * 1e10
+    farthest = start.clone()
+    batch = torch.arange(B, dtype=torch.long, device=xyz.device)
+    for i in range(npoint):
+        centroids[:, i] = farthest
+        centroid = xyz[batch, farthest, :].view(B, 1, 3)
+        dist = torch.sum((xyz - centroid) ** 2, -1)
+        mask = dist < distance
+        distance[mask] = dist[mask]
+        farthest = torch.max(distance, -1)[1]
+    return centroids
+
+
+def query_ball_point(radius, nsample, xyz, new_xyz):
+    """:87-107  mark > r^2 as N, SORT the [B,S,N] index tensor, keep the first nsample, pad with the first."""
+    B, N, _ = xyz.shape
+    S = new_xyz.shape[1]
+    group_idx = torch.arange(N, dtype=torch.long, device=xyz.device).view(1, 1, N).repeat([B, S, 1])
+    group_idx[square_distance(new_xyz, xyz) > radius ** 2] = N
+    group_idx = group_idx.sort(dim=-1)[0][:, :, :nsample]
+    first = group_idx[:, :, 0].view(B, S, 1).repeat([1, 1, nsample])
+    mask = group_idx == N
+    group_idx[mask] = first[mask]
+    return group_idx

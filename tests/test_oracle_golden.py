@@ -186,3 +186,23 @@ def test_edge_feature_port_matches_reference(golden):
         assert np.array_equal(feat.detach().numpy(), g[f"{tag}_feat"]), tag
         (feat * torch.randn(feat.shape, generator=gen)).sum().backward()
         assert np.array_equal(x.grad.numpy(), g[f"{tag}_grad"]), tag
+
+
+def test_torch_seam_port_matches_reference(golden):
+    """oracle/torch_port.py's restatement of model/pointnet2_utils.py:19-107 (what tools/bench_ops.py and the config-3
+    benchmark time as "the reference's torch program") reproduces the reference's outputs bit for bit."""
+    import torch
+    from oracle import torch_port as tp
+
+    g = golden("torch_seams")
+    xyz = torch.from_numpy(g["xyz"])
+    fps = tp.farthest_point_sample(xyz, 64, torch.from_numpy(g["fps_start"]))
+    assert np.array_equal(fps.numpy(), g["fps_idx"])
+    new_xyz = tp.index_points(xyz, fps)
+    assert np.array_equal(new_xyz.numpy(), g["new_xyz"])
+    assert np.array_equal(tp.square_distance(new_xyz, xyz).numpy(), g["sqdist"])
+    for key in g.files:
+        if key.startswith("ball_"):
+            r, ns = float(key.split("_")[1][1:]), int(key.split("_")[2][2:])
+            assert np.array_equal(tp.query_ball_point(r, ns, xyz, new_xyz).numpy(), g[key]), key
+    assert np.array_equal(tp.index_points(xyz, torch.from_numpy(g["ball_r0.2_ns32"])).numpy(), g["index_points_grouped"])

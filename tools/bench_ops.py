@@ -77,15 +77,38 @@ def main():
         t_new = timeit(lambda: _ext.furthest_point_sampling(xyz, npoint))
         t_ref = timeit(lambda: ref.furthest_point_sampling(xyz, npoint)) if ref else None
         row(f"furthest_point_sampling B={B} N={N} npoint={npoint}", t_new, t_ref, extra={"rounds_per_s": B * npoint / t_new * 1e3})
+    from oracle import torch_port as tp
+
     start = torch.randint(0, N, (B,), device="cuda")
-    row(f"torch-semantics FPS B={B} N={N} npoint=512", timeit(lambda: F.fps_torch(xyz, 512, start)), None)
+    row(f"torch-semantics FPS B={B} N={N} npoint=512", timeit(lambda: F.fps_torch(xyz, 512, start)),
+        timeit(lambda: tp.farthest_point_sample(xyz, 512, start), iters=3), extra={"ref": "reference torch program (512 rounds of ~8 kernels) on the same GPU"})
     fps = _ext.furthest_point_sampling(xyz, 512)
     new_xyz = _ext.gather_points(xyz.transpose(1, 2).contiguous(), fps).transpose(1, 2).contiguous()
     for (r, ns) in ((0.2, 32), (0.4, 64)):
         t_new = timeit(lambda: _ext.ball_query(new_xyz, xyz, r, ns))
         t_ref = timeit(lambda: ref.ball_query(new_xyz, xyz, r, ns)) if ref else None
         row(f"ball_query B={B} N={N} S=512 r={r} ns={ns}", t_new, t_ref, bytes_alg=B * (N + 512) * 12 + B * 512 * ns * 4)
-    row(f"torch-semantics query_ball_point B={B} N={N} S=512 r=0.2 ns=32", timeit(lambda: ms.query_ball_point(0.2, 32, xyz, new_xyz)), None)
+    row(f"torch-semantics query_ball_point B={B} N={N} S=512 r=0.2 ns=32", timeit(lambda: ms.query_ball_point(0.2, 32, xyz, new_xyz)),
+        timeit(lambda: tp.query_ball_point(0.2, 32, xyz, new_xyz)), extra={"ref": "reference torch program (int64 [B,S,N] sort) on the same GPU"})
+    bidx = ms.query_ball_point(0.2, 32, xyz, new_xyz)
+    row(f"torch-semantics index_points (group) B={B} N={N} S=512 ns=32 C=3", timeit(lambda: ms.index_points(xyz, bidx)),
+        timeit(lambda: tp.index_points(xyz, bidx)), extra={"ref": "reference torch program (advanced indexing) on the same GPU"})
+    row(f"torch-semantics square_distance B={B} S=512 N={N}", timeit(lambda: ms.square_distance(new_xyz, xyz)),
+        timeit(lambda: tp.square_distance(new_xyz, xyz)), bytes_alg=4 * B * 512 * N, extra={"ref": "reference torch program (matmul + 2 adds) on the same GPU"})
+    # the whole set-abstraction front end of PointNet++ SSG level 1 (model/pointnet2_utils.py:110-138 sample_and_group)
+    feats = torch.randn(B, N, 3, device="cuda")
+
+    def sag(fps_fn, ball_fn, idx_fn):
+        f = fps_fn(xyz, 512, start)
+        nx = idx_fn(xyz, f)
+        gi = ball_fn(0.2, 32, xyz, nx)
+        g = idx_fn(xyz, gi) - nx.view(B, 512, 1, 3)
+        return torch.cat([g, idx_fn(feats, gi)], dim=-1)
+
+    row(f"sample_and_group (SSG level 1) B={B} N={N} npoint=512 r=0.2 ns=32",
+        timeit(lambda: sag(F.fps_torch, ms.query_ball_point, ms.index_points)),
+        timeit(lambda: sag(tp.farthest_point_sample, tp.query_ball_point, tp.index_points), iters=3),
+        extra={"ref": "reference torch program on the same GPU"})
     for (C, S, ns, n) in ((3, 512, 32, 1024), (131, 128, 64, 512), (64, 512, 32, 1024)):
         pts = torch.randn(B, C, n, device="cuda")
         idx = torch.randint(0, n, (B, S, ns), device="cuda", dtype=torch.int32)
