@@ -68,8 +68,11 @@ __global__ void __launch_bounds__(256) edge_keys_kernel(const long long *__restr
 // ---- backward: one CTA per (b,c) plane.  Thread n streams row n of both halves (k contiguous floats: a warp
 // covers 32*k contiguous floats), keeps sum_t (gB - gA) in a register and parks the gA row in shared memory; after
 // a barrier the incoming edges are summed from shared memory in ascending edge order.
+constexpr int kHubSplit = 32;
+constexpr int kGradThreads = 512;  // two CTAs of 512 per SM (80 KB of shared memory each at N*k = 20480): the three
+                                   // dependent phases of a plane are latency-bound, so more rows in flight per phase
 template <bool STAGED>
-__global__ void __launch_bounds__(256) edge_feature_grad_kernel(const float *__restrict__ g,
+__global__ void __launch_bounds__(kGradThreads) edge_feature_grad_kernel(const float *__restrict__ g,
                                                                 const int *__restrict__ off,
                                                                 const int *__restrict__ list, int C, int N, int k,
                                                                 long long planes, float *__restrict__ grad_x) {
@@ -85,7 +88,7 @@ __global__ void __launch_bounds__(256) edge_feature_grad_kernel(const float *__r
     const int *l = list + (size_t)b * E;
     float *dst = grad_x + (size_t)bc * N;
     __syncthreads();
-    for (int n0 = 0; n0 < N; n0 += 256) {
+    for (int n0 = 0; n0 < N; n0 += kGradThreads) {
       const int n = n0 + threadIdx.x;
       float own = 0.f;
       if (n < N) {
@@ -116,20 +119,39 @@ __global__ void __launch_bounds__(256) edge_feature_grad_kernel(const float *__r
       if (STAGED && n < N) dst[n] = own;  // finished below
     }
     if (STAGED) {
+      // kNN graphs of learned features have hubs (in-degrees in the hundreds next to a mean of k): a thread sums at most
+      // kHubSplit incoming edges of its point; what is left of a hub is summed by a whole warp afterwards (lanes
+      // stride the rest of the segment, fixed-order tree) -- same bits on every run, no lane waits for a hub.
+      int *hubq = reinterpret_cast<int *>(sA + E);  // [N] points with more than kHubSplit incoming edges
+      __shared__ int nhub;
+      if (threadIdx.x == 0) nhub = 0;
       __syncthreads();
-      for (int n = threadIdx.x; n < N; n += 256) {
+      for (int n = threadIdx.x; n < N; n += kGradThreads) {
         float acc = dst[n];
         const int q1 = o[n + 1];
         int q = o[n];
-        for (; q + 3 < q1; q += 4) {  // four list entries in flight
+        const int qe = min(q1, q + kHubSplit);
+        for (; q + 3 < qe; q += 4) {  // four list entries in flight
           const int e0 = __ldg(l + q), e1 = __ldg(l + q + 1), e2 = __ldg(l + q + 2), e3 = __ldg(l + q + 3);
           acc += sA[e0];
           acc += sA[e1];
           acc += sA[e2];
           acc += sA[e3];
         }
-        for (; q < q1; ++q) acc += sA[__ldg(l + q)];
+        for (; q < qe; ++q) acc += sA[__ldg(l + q)];
         dst[n] = acc;
+        if (q1 > qe) hubq[atomicAdd(&nhub, 1)] = n;
+      }
+      __syncthreads();
+      const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+      for (int h = warp; h < nhub; h += kGradThreads / 32) {
+        const int n = hubq[h];
+        const int q1 = o[n + 1];
+        float part = 0.f;
+        for (int q = o[n] + kHubSplit + lane; q < q1; q += 32) part += sA[__ldg(l + q)];
+#pragma unroll
+        for (int st = 16; st > 0; st >>= 1) part += __shfl_down_sync(0xffffffffu, part, st);
+        if (lane == 0) dst[n] += part;
       }
     }
   }
@@ -196,7 +218,7 @@ HG_API int hg_edge_feature_grad_f32(const float *grad_out, const int64_t *idx, i
   int rc = hg_csr_build(keys, B, E, N, csr_ws, hg_csr_stable_workspace_bytes(B, N, E), &csr, stream);
   if (rc) return rc;
   const long long planes = (long long)B * C;
-  const size_t smem = (size_t)E * sizeof(float);
+  const size_t smem = ((size_t)E + (size_t)N) * sizeof(float);  // gA plane + hub queue
   const bool staged = smem <= 200 * 1024;
   long long grid = planes;
   const long long cap = (long long)hg_sm_count() * 8;
@@ -204,9 +226,9 @@ HG_API int hg_edge_feature_grad_f32(const float *grad_out, const int64_t *idx, i
   if (staged) {
     if (smem > 48 * 1024)
       HG_CUDA(cudaFuncSetAttribute(edge_feature_grad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    edge_feature_grad_kernel<true><<<(int)grid, 256, smem, stream>>>(grad_out, csr.off, csr.list, C, N, k, planes, grad_x);
+    edge_feature_grad_kernel<true><<<(int)grid, kGradThreads, smem, stream>>>(grad_out, csr.off, csr.list, C, N, k, planes, grad_x);
   } else {
-    edge_feature_grad_kernel<false><<<(int)grid, 256, 0, stream>>>(grad_out, csr.off, csr.list, C, N, k, planes, grad_x);
+    edge_feature_grad_kernel<false><<<(int)grid, kGradThreads, 0, stream>>>(grad_out, csr.off, csr.list, C, N, k, planes, grad_x);
   }
   HG_CHECK_LAUNCH("edge_feature_grad_kernel");
   return HG_OK;
