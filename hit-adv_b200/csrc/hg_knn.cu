@@ -87,40 +87,93 @@ __global__ void __launch_bounds__(256) knn_dist_generic_kernel(const float *__re
   }
 }
 
-// Warp per row: k1 rounds of "smallest (value, index) strictly after the previous pick".
+// Warp per row.  The k1 smallest (value, index) pairs of a row of K distances, ascending, lowest index first on ties.
+//   1. every lane takes the minimum of its K/32 strided elements; the k1-th smallest of those 32 lane minima (one
+//      warp-wide bitonic sort) is an upper bound tau on the row's k1-th smallest value (k1 <= 32 distinct elements
+//      are <= tau);
+//   2. the elements <= tau -- typically 1.5-2 k1 of them -- are compacted in index order into a small candidate
+//      buffer (ballot + prefix popcount);
+//   3. k1 rounds of "smallest (value, index) strictly after the previous pick" run over the candidates only.
+// The first version ran step 3 over the whole row (k1 x K/32 steps per lane).  If the candidates overflow the buffer
+// (heavy ties), the row falls back to exactly that.
+constexpr int kSelCap = 128;  // candidates per row kept in shared memory (4 per lane)
+
+__device__ __forceinline__ void knn_select_rounds(const float *__restrict__ v, const int *__restrict__ id, int n,
+                                                  int k1, int lane, float *__restrict__ vals, int *__restrict__ idx,
+                                                  size_t out) {
+  float pv = -CUDART_INF_F;
+  int pj = -1;
+  for (int t = 0; t < k1; ++t) {
+    float bv = CUDART_INF_F;
+    int bj = 0x7fffffff;
+    for (int q = lane; q < n; q += 32) {
+      const float x = v[q];
+      const int j = id ? id[q] : q;
+      const bool after = (x > pv) || (x == pv && j > pj);
+      if (after && (x < bv || (x == bv && j < bj))) {
+        bv = x;
+        bj = j;
+      }
+    }
+    const float wv = hg_warp_min_f32(bv);
+    const int wj = __reduce_min_sync(0xffffffffu, (bv == wv) ? bj : 0x7fffffff);
+    pv = wv;
+    pj = wj;
+    if (lane == 0) {
+      if (vals) vals[out + t] = wv;
+      idx[out + t] = wj;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(128) knn_select_rows_kernel(const float *__restrict__ dist, int nrows, int K,
                                                               int k1, float *__restrict__ vals,
                                                               int *__restrict__ idx) {
-  extern __shared__ float rowbuf[];  // [4 warps][K]
+  extern __shared__ float rowbuf[];  // [4 warps][K] rows, then [4][kSelCap] candidate values, [4][kSelCap] indices
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float *row = rowbuf + (size_t)warp * K;
+  float *cv = rowbuf + (size_t)4 * K + (size_t)warp * kSelCap;
+  int *ci = reinterpret_cast<int *>(rowbuf + (size_t)4 * K + (size_t)4 * kSelCap) + (size_t)warp * kSelCap;
   for (int r = blockIdx.x * 4 + warp; r < nrows; r += gridDim.x * 4) {
     __syncwarp();
-    for (int j = lane; j < K; j += 32) row[j] = dist[(size_t)r * K + j];
-    __syncwarp();
-    float pv = -CUDART_INF_F;
-    int pj = -1;
-    for (int t = 0; t < k1; ++t) {
-      float bv = CUDART_INF_F;
-      int bj = 0x7fffffff;
-      for (int j = lane; j < K; j += 32) {
-        const float v = row[j];
-        const bool after = (v > pv) || (v == pv && j > pj);
-        if (after && (v < bv)) {  // ascending j per lane: strict '<' keeps the lowest index
-          bv = v;
-          bj = j;
-        }
-      }
-      const float wv = hg_warp_min_f32(bv);
-      const int cand = (bv == wv) ? bj : 0x7fffffff;
-      const int wj = __reduce_min_sync(0xffffffffu, cand);
-      pv = wv;
-      pj = wj;
-      if (lane == 0) {
-        if (vals) vals[(size_t)r * k1 + t] = wv;
-        idx[(size_t)r * k1 + t] = wj;
+    float lmin = CUDART_INF_F;
+    for (int j = lane; j < K; j += 32) {
+      const float x = dist[(size_t)r * K + j];
+      row[j] = x;
+      lmin = fminf(lmin, x);
+    }
+    // bitonic sort of the 32 lane minima across the warp (ascending by lane)
+    float s = lmin;
+#pragma unroll
+    for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+      for (int stride = size >> 1; stride > 0; stride >>= 1) {
+        const float o = __shfl_xor_sync(0xffffffffu, s, stride);
+        const bool up = ((lane & size) == 0);         // ascending block
+        const bool lower = ((lane & stride) == 0);    // this lane keeps the smaller of the pair in an ascending block
+        s = (up == lower) ? fminf(s, o) : fmaxf(s, o);
       }
     }
+    const float tau = __shfl_sync(0xffffffffu, s, k1 - 1);
+    __syncwarp();
+    int cnt = 0;
+    for (int j0 = 0; j0 < K; j0 += 32) {
+      const int j = j0 + lane;
+      const float x = (j < K) ? row[j] : CUDART_INF_F;
+      const bool keep = (j < K) && (x <= tau);
+      const unsigned m = __ballot_sync(0xffffffffu, keep);
+      const int pos = cnt + __popc(m & ((1u << lane) - 1u));
+      if (keep && pos < kSelCap) {
+        cv[pos] = x;
+        ci[pos] = j;
+      }
+      cnt += __popc(m);
+    }
+    __syncwarp();
+    if (cnt <= kSelCap)
+      knn_select_rounds(cv, ci, cnt, k1, lane, vals, idx, (size_t)r * k1);
+    else
+      knn_select_rounds(row, nullptr, K, k1, lane, vals, idx, (size_t)r * k1);
   }
 }
 
@@ -272,7 +325,7 @@ HG_API int hg_knn_self_f32(const float *pc, int B, int K, int C, int k1, float *
   const size_t per = (size_t)K * K * sizeof(float);
   int nb = (int)(kGenericScratchBytes / per);
   if (nb < 1) nb = 1;
-  const size_t sel_smem = (size_t)4 * K * sizeof(float);
+  const size_t sel_smem = ((size_t)4 * K + (size_t)8 * kSelCap) * sizeof(float);
   if (sel_smem > 48 * 1024)
     HG_CUDA(cudaFuncSetAttribute(knn_select_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem));
   for (int b0 = 0; b0 < B; b0 += nb) {

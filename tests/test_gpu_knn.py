@@ -145,3 +145,15 @@ def test_knn_folded_filter_is_conservative_far_from_origin(oracle, F, k1):
         vals, idx = F.knn_self(gpu(pc), k1)
         ov, oi = oracle.knn_self(pc, k1, threads=4)
         assert np.array_equal(vals.cpu().numpy(), ov) and np.array_equal(idx.cpu().numpy(), oi), (offset, scale)
+
+
+def test_knn_generic_c_heavy_ties(oracle, F):
+    """Feature clouds with massive exact ties (every point one of four prototypes): the row select's candidate buffer
+    overflows and it falls back to the full-row rounds; values and lowest-index-first order must still be the oracle's."""
+    rng = np.random.default_rng(5)
+    protos = rng.standard_normal((4, 16)).astype(np.float32)
+    pc = protos[rng.integers(0, 4, size=(2, 600))]  # [2,600,16]
+    pc[1, :300] = protos[0]
+    vals, idx = F.knn_self(gpu(pc), 20)
+    ov, oi = oracle.knn_self(pc, 20, threads=2)
+    assert np.array_equal(vals.cpu().numpy(), ov) and np.array_equal(idx.cpu().numpy(), oi)
