@@ -36,53 +36,89 @@ __global__ void knn_sumsq_kernel(const float *__restrict__ pc, long long total, 
   }
 }
 
-// dist tile: 64x64 per CTA, 4x4 per thread, channels consumed strictly in order (sequential FMA chain).
-constexpr int kGT = 64, kGC = 16;
+// dist tile: 128 rows x 64 columns per CTA, 8 x 4 per thread (columns as two packed pairs), channels consumed strictly
+// in order: every accumulator is the reference's sequential FMA chain (product of channel 0 first, then c = 1..C-1).
+// Per channel a thread reads 8 row values (two broadcast LDS.128) and 4 column values (one LDS.128) for 16 FFMA2:
+// FMA-bound, where the first version (4 x 4 scalar, 8 LDS.32 per 16 FFMA) was LSU-bound.
+constexpr int kGTM = 128, kGTN = 64, kGC = 16;
 __global__ void __launch_bounds__(256) knn_dist_generic_kernel(const float *__restrict__ pc,
                                                                const float *__restrict__ xx, int K, int C,
                                                                float *__restrict__ dist /*[nb,K,K]*/) {
-  __shared__ float As[kGC][kGT + 1], Bs[kGC][kGT + 1];
+  __shared__ __align__(16) float As[kGC][kGTM], Bs[kGC][kGTN];
   const int b = blockIdx.z;
   const float *p = pc + (size_t)b * K * C;
-  const int i0 = blockIdx.y * kGT, j0 = blockIdx.x * kGT;
+  const int i0 = blockIdx.y * kGTM, j0 = blockIdx.x * kGTN;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  float acc[4][4];
+  float2 acc[8][2];
 #pragma unroll
-  for (int u = 0; u < 4; ++u)
-#pragma unroll
-    for (int v = 0; v < 4; ++v) acc[u][v] = 0.f;
+  for (int u = 0; u < 8; ++u) acc[u][0] = acc[u][1] = make_float2(0.f, 0.f);
+  const bool vec_ok = (C & 3) == 0 && (reinterpret_cast<uintptr_t>(pc) & 15) == 0;
   for (int c0 = 0; c0 < C; c0 += kGC) {
     __syncthreads();
-    for (int t = threadIdx.x; t < kGT * kGC; t += 256) {
-      const int rrow = t / kGC, cc = t % kGC;
-      const int c = c0 + cc;
-      As[cc][rrow] = (i0 + rrow < K && c < C) ? p[(size_t)(i0 + rrow) * C + c] : 0.f;
-      Bs[cc][rrow] = (j0 + rrow < K && c < C) ? p[(size_t)(j0 + rrow) * C + c] : 0.f;
+    // stage kGC channels of the 128 rows and the 64 columns, transposed to [channel][point]
+    for (int t = threadIdx.x; t < (kGTM + kGTN) * (kGC / 4); t += 256) {
+      const int pt = t % (kGTM + kGTN), q = t / (kGTM + kGTN);
+      const bool isA = pt < kGTM;
+      const int row = isA ? i0 + pt : j0 + (pt - kGTM);
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int c = c0 + 4 * q;
+      if (row < K) {
+        const float *src = p + (size_t)row * C + c;
+        if (vec_ok && c + 3 < C) {
+          v = *reinterpret_cast<const float4 *>(src);
+        } else {
+          if (c < C) v.x = src[0];
+          if (c + 1 < C) v.y = src[1];
+          if (c + 2 < C) v.z = src[2];
+          if (c + 3 < C) v.w = src[3];
+        }
+      }
+      float *dstp = isA ? &As[4 * q][pt] : &Bs[4 * q][pt - kGTM];
+      const int ld = isA ? kGTM : kGTN;
+      dstp[0] = v.x;
+      dstp[ld] = v.y;
+      dstp[2 * ld] = v.z;
+      dstp[3 * ld] = v.w;
     }
     __syncthreads();
     const int cl = min(kGC, C - c0);
+#pragma unroll 4
     for (int cc = 0; cc < cl; ++cc) {
-      float a[4], bb[4];
+      const float4 a0 = *reinterpret_cast<const float4 *>(&As[cc][ty * 8]);
+      const float4 a1 = *reinterpret_cast<const float4 *>(&As[cc][ty * 8 + 4]);
+      const float4 bb = *reinterpret_cast<const float4 *>(&Bs[cc][tx * 4]);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float2 b01 = make_float2(bb.x, bb.y), b23 = make_float2(bb.z, bb.w);
 #pragma unroll
-      for (int u = 0; u < 4; ++u) a[u] = As[cc][ty * 4 + u];
-#pragma unroll
-      for (int v = 0; v < 4; ++v) bb[v] = Bs[cc][tx * 4 + v];
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-#pragma unroll
-        for (int v = 0; v < 4; ++v) acc[u][v] = __fmaf_rn(a[u], bb[v], acc[u][v]);
+      for (int u = 0; u < 8; ++u) {
+        acc[u][0] = __ffma2_rn(make_float2(a[u], a[u]), b01, acc[u][0]);
+        acc[u][1] = __ffma2_rn(make_float2(a[u], a[u]), b23, acc[u][1]);
+      }
     }
   }
   const float *xb = xx + (size_t)b * K;
+  const int j = j0 + tx * 4;
+  float xj[4];
 #pragma unroll
-  for (int u = 0; u < 4; ++u) {
-    const int i = i0 + ty * 4 + u;
+  for (int v = 0; v < 4; ++v) xj[v] = (j + v < K) ? xb[j + v] : 0.f;
+  const bool vst = (K & 3) == 0 && (reinterpret_cast<uintptr_t>(dist) & 15) == 0 && j + 3 < K;
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const int i = i0 + ty * 8 + u;
     if (i >= K) continue;
+    const float xi = xb[i];
+    float o[4];
+    o[0] = __fadd_rn(__fadd_rn(xj[0], __fmul_rn(-2.0f, acc[u][0].x)), xi);
+    o[1] = __fadd_rn(__fadd_rn(xj[1], __fmul_rn(-2.0f, acc[u][0].y)), xi);
+    o[2] = __fadd_rn(__fadd_rn(xj[2], __fmul_rn(-2.0f, acc[u][1].x)), xi);
+    o[3] = __fadd_rn(__fadd_rn(xj[3], __fmul_rn(-2.0f, acc[u][1].y)), xi);
+    float *dp = dist + ((size_t)b * K + i) * K + j;
+    if (vst) {
+      *reinterpret_cast<float4 *>(dp) = make_float4(o[0], o[1], o[2], o[3]);
+    } else {
 #pragma unroll
-    for (int v = 0; v < 4; ++v) {
-      const int j = j0 + tx * 4 + v;
-      if (j >= K) continue;
-      dist[((size_t)b * K + i) * K + j] = __fadd_rn(__fadd_rn(xb[j], __fmul_rn(-2.0f, acc[u][v])), xb[i]);
+      for (int v = 0; v < 4; ++v)
+        if (j + v < K) dp[v] = o[v];
     }
   }
 }
@@ -330,7 +366,7 @@ HG_API int hg_knn_self_f32(const float *pc, int B, int K, int C, int k1, float *
     HG_CUDA(cudaFuncSetAttribute(knn_select_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem));
   for (int b0 = 0; b0 < B; b0 += nb) {
     const int cb = (B - b0 < nb) ? (B - b0) : nb;
-    dim3 grid((K + kGT - 1) / kGT, (K + kGT - 1) / kGT, cb);
+    dim3 grid((K + kGTN - 1) / kGTN, (K + kGTM - 1) / kGTM, cb);
     knn_dist_generic_kernel<<<grid, 256, 0, stream>>>(pc + (size_t)b0 * K * C, xx + (size_t)b0 * K, K, C, dist);
     HG_CHECK_LAUNCH("knn_dist_generic_kernel");
     const int nrows = cb * K;
