@@ -305,15 +305,21 @@ int launch_form(const float *q, const float *r, int B, int Nq, int Nr, int k1, f
     hg_set_error("knn: k=%d outside [1,32]", k1);
     return HG_E_UNSUPPORTED;
   }
-  // queries per lane: amortise the candidate loads, but keep small query sets spread over the machine and the
-  // register-resident lists (2*KM registers per query) within budget
+  // queries per lane: amortise the candidate loads, but keep small query sets spread over the machine -- at least
+  // ~2 CTAs per SM, a small batch (DGCNN: 32 clouds) is latency-bound on its longest CTA -- and the register-resident
+  // lists (2*KM registers per query) within budget
+  const long long want = 2LL * hg_sm_count();
+  auto ctas = [&](int qt) { return (long long)B * ((Nq + qt * kThreads - 1) / (qt * kThreads)); };
   if (k1 <= 6) {
-    if (Nq >= 3 * kThreads) return launch_qt<FORM, 4, 6, IdxT>(q, r, B, Nq, Nr, k1, vals, idx, thr0, sbound, stream);
-    if (Nq > kThreads) return launch_qt<FORM, 2, 6, IdxT>(q, r, B, Nq, Nr, k1, vals, idx, thr0, sbound, stream);
+    if (Nq >= 3 * kThreads && ctas(4) >= want)
+      return launch_qt<FORM, 4, 6, IdxT>(q, r, B, Nq, Nr, k1, vals, idx, thr0, sbound, stream);
+    if (Nq > kThreads && ctas(2) >= want)
+      return launch_qt<FORM, 2, 6, IdxT>(q, r, B, Nq, Nr, k1, vals, idx, thr0, sbound, stream);
     return launch_qt<FORM, 1, 6, IdxT>(q, r, B, Nq, Nr, k1, vals, idx, thr0, sbound, stream);
   }
   if (k1 <= 20) {
-    if (Nq > kThreads) return launch_qt<FORM, 2, 20, IdxT>(q, r, B, Nq, Nr, k1, vals, idx, thr0, sbound, stream);
+    if (Nq > kThreads && ctas(2) >= want)
+      return launch_qt<FORM, 2, 20, IdxT>(q, r, B, Nq, Nr, k1, vals, idx, thr0, sbound, stream);
     return launch_qt<FORM, 1, 20, IdxT>(q, r, B, Nq, Nr, k1, vals, idx, thr0, sbound, stream);
   }
   return launch_qt<FORM, 1, 32, IdxT>(q, r, B, Nq, Nr, k1, vals, idx, thr0, sbound, stream);
