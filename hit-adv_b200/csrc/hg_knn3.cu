@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(kThreads) knn3_kernel(const float *__restrict_
       const int cnt = min(step, ngroups - g0);
       // ---- main loop: packed filter values, sign bits OR-ed per group and shifted into the query's mask ------
       // (after cnt shifts, bit cnt-1-g belongs to group g0+g)
-#pragma unroll 1
+#pragma unroll (KM <= 6 ? 2 : 1)
       for (int g = 0; g < cnt; ++g) {
         const float4 *cp = cand + 2 * GP * (g0 + g);
         float4 cA[GP], cB[GP];
@@ -305,20 +305,22 @@ int launch_form(const float *q, const float *r, int B, int Nq, int Nr, int k1, f
     hg_set_error("knn: k=%d outside [1,32]", k1);
     return HG_E_UNSUPPORTED;
   }
-  // queries per lane: amortise the candidate loads, but keep small query sets spread over the machine -- at least
-  // ~2 CTAs per SM, a small batch (DGCNN: 32 clouds) is latency-bound on its longest CTA -- and the register-resident
-  // lists (2*KM registers per query) within budget
+  // Queries per lane (QT): more queries amortise the candidate loads (LDS per pair halves with every doubling), which
+  // pays on long candidate lists; on short ones (< 2k candidates) the cold-start drains dominate and run one query
+  // after the other, so fewer queries per lane win (measured, k+1 = 6: 16384 points 5.96 / 6.33 / 8.72 ms for QT = 4 /
+  // 2 / 1; 1024 points 2.46 / 2.14 / 2.28 ms).  Small batches additionally drop QT until the grid fills the machine.
   const long long want = 2LL * hg_sm_count();
   auto ctas = [&](int qt) { return (long long)B * ((Nq + qt * kThreads - 1) / (qt * kThreads)); };
+  const bool short_list = Nr < 2048;
   if (k1 <= 6) {
-    if (Nq >= 3 * kThreads && ctas(4) >= want)
+    if (!short_list && Nq >= 3 * kThreads && ctas(4) >= want)
       return launch_qt<FORM, 4, 6, IdxT>(q, r, B, Nq, Nr, k1, vals, idx, thr0, sbound, stream);
     if (Nq > kThreads && ctas(2) >= want)
       return launch_qt<FORM, 2, 6, IdxT>(q, r, B, Nq, Nr, k1, vals, idx, thr0, sbound, stream);
     return launch_qt<FORM, 1, 6, IdxT>(q, r, B, Nq, Nr, k1, vals, idx, thr0, sbound, stream);
   }
   if (k1 <= 20) {
-    if (Nq > kThreads && ctas(2) >= want)
+    if (!short_list && Nq > kThreads && ctas(2) >= want)
       return launch_qt<FORM, 2, 20, IdxT>(q, r, B, Nq, Nr, k1, vals, idx, thr0, sbound, stream);
     return launch_qt<FORM, 1, 20, IdxT>(q, r, B, Nq, Nr, k1, vals, idx, thr0, sbound, stream);
   }
