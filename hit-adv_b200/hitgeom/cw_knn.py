@@ -39,6 +39,7 @@ class CWKNN:
         # device instead of in Python doubles -- a 1e-7 relative difference in the step size)
         self.capturable_adam = graph if capturable_adam is None else capturable_adam
         self.loop_ms = 0.0  # device time of the iteration loop of the last attack() (for the benchmark)
+        self.replay_ms, self.replays = 0.0, 0  # of which: the graph-replayed iterations
 
     # -- pieces ------------------------------------------------------------------------------------------------
     def _logits(self, adv_data):
@@ -93,6 +94,7 @@ class CWKNN:
                 it, self.num_iter, int(s[0]), B, s[1], s[2]))
 
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        eg = torch.cuda.Event(enable_timing=True)
         args = (adv_data, ori_data, ori_t, normal, target, opt, stats)
         graph, warm = None, min(3, self.num_iter)
         e0.record()
@@ -106,6 +108,7 @@ class CWKNN:
                     with torch.cuda.graph(graph, stream=side):
                         self._step(*args)
                 torch.cuda.current_stream().wait_stream(side)
+                eg.record()
             if graph is not None:  # (capture records the iteration without running it)
                 graph.replay()
             else:
@@ -118,6 +121,8 @@ class CWKNN:
             pred = torch.argmax(self._logits(adv_data), dim=-1)
             success_num = int(self._success(pred, target).sum().item())
         self.loop_ms = e0.elapsed_time(e1)
+        self.replays = max(self.num_iter - warm, 0) if graph is not None else 0
+        self.replay_ms = eg.elapsed_time(e1) if graph is not None else 0.0
         if self.verbose:
             print('Successfully attack {}/{}'.format(success_num, B))
         return adv_data.detach().transpose(1, 2).contiguous().cpu().numpy(), success_num
