@@ -432,27 +432,57 @@ __global__ void __launch_bounds__(128) knn_seed_kernel(const float4 *__restrict_
   float v[KM];
 #pragma unroll
   for (int t = 0; t < KM; ++t) v[t] = CUDART_INF_F;
-  int seen = 0;
-  for (int z = lo[2]; z <= hi[2] && seen < kMaxSeedCand; ++z)
-    for (int y = lo[1]; y <= hi[1] && seen < kMaxSeedCand; ++y) {
-      if (z < 0 || z >= G || y < 0 || y >= G) continue;
-      const int x0 = max(lo[0], 0), x1 = min(hi[0], G - 1);
-      const int c0 = (z * G + y) * G + x0, c1 = (z * G + y) * G + x1;
-      for (int t = o[c0]; t < o[c1 + 1] && seen < kMaxSeedCand; ++t, ++seen) {
-        const float4 r = pts[t];
-        const float d = knn_dist_exact<HG_KNN_FORM_EXPANDED>(a0, a1, a2, a3, r.x, r.y, r.z, r.w);
-        if (d < v[KM - 1]) {
-          v[KM - 1] = d;
+  // the (up to 9) runs of x-adjacent cells: all their bounds are loaded before the first candidate (independent loads,
+  // one latency instead of one per run)
+  int rb[9], re[9];
+  int nruns = 0;
 #pragma unroll
-          for (int u = KM - 1; u > 0; --u)
-            if (v[u] < v[u - 1]) {
-              const float tv = v[u];
-              v[u] = v[u - 1];
-              v[u - 1] = tv;
-            }
-        }
+  for (int zz = 0; zz < 3; ++zz)
+#pragma unroll
+    for (int yy = 0; yy < 3; ++yy) {
+      const int z = lo[2] + zz, y = lo[1] + yy;
+      const bool ok = z <= hi[2] && y <= hi[1] && z >= 0 && z < G && y >= 0 && y < G;
+      const int x0 = max(lo[0], 0), x1 = min(hi[0], G - 1);
+      const int c0 = ok ? (z * G + y) * G + x0 : 0, c1 = ok ? (z * G + y) * G + x1 : -1;
+      rb[zz * 3 + yy] = ok ? o[c0] : 0;
+      re[zz * 3 + yy] = ok ? o[c1 + 1] : 0;
+      nruns += ok;
+    }
+  (void)nruns;
+  int seen = 0;
+#pragma unroll
+  for (int rI = 0; rI < 9; ++rI) {
+    int t = rb[rI];
+    const int te = min(re[rI], t + (kMaxSeedCand - seen));
+    seen += max(te - t, 0);
+    for (; t + 1 < te; t += 2) {  // two candidates in flight; insertion without branches (values only)
+      const float4 r0 = pts[t], r1 = pts[t + 1];
+      float d0 = knn_dist_exact<HG_KNN_FORM_EXPANDED>(a0, a1, a2, a3, r0.x, r0.y, r0.z, r0.w);
+      float d1 = knn_dist_exact<HG_KNN_FORM_EXPANDED>(a0, a1, a2, a3, r1.x, r1.y, r1.z, r1.w);
+#pragma unroll
+      for (int u = 0; u < KM; ++u) {  // v stays sorted ascending: each level keeps the smaller, passes the larger on
+        const float lo0 = fminf(v[u], d0);
+        d0 = fmaxf(v[u], d0);
+        v[u] = lo0;
+      }
+#pragma unroll
+      for (int u = 0; u < KM; ++u) {
+        const float lo1 = fminf(v[u], d1);
+        d1 = fmaxf(v[u], d1);
+        v[u] = lo1;
       }
     }
+    if (t < te) {
+      const float4 r0 = pts[t];
+      float d0 = knn_dist_exact<HG_KNN_FORM_EXPANDED>(a0, a1, a2, a3, r0.x, r0.y, r0.z, r0.w);
+#pragma unroll
+      for (int u = 0; u < KM; ++u) {
+        const float lo0 = fminf(v[u], d0);
+        d0 = fmaxf(v[u], d0);
+        v[u] = lo0;
+      }
+    }
+  }
   const float bound = v[KM - 1];
   thr0[(size_t)b * N + list[(size_t)b * N + s_q]] = (bound < CUDART_INF_F) ? nextafterf(bound, CUDART_INF_F) : CUDART_INF_F;
 }
@@ -551,9 +581,10 @@ int hg_knn3_self_seeded_i32(const float *pc, int B, int N, int k1, float *vals, 
     HG_CHECK_LAUNCH("knn_cell_sort_kernel");
   }
   dim3 grid((N + 127) / 128, B);
-  // neighbourhood of the seed scan: the 2x2x2 cells nearest to the query for short lists (3.4x fewer candidates, a
-  // slightly looser bound: measured 5-9 % faster end to end at k+1 = 6), all 27 cells for k+1 > 6 (tools/knn_seed_sweep.py)
-  const int near8 = g_seed_near8 == 1 ? 1 : g_seed_near8 == 2 ? 0 : (k1 <= 6);
+  // neighbourhood of the seed scan: the 2x2x2 cells nearest to the query (3.4x fewer candidates, a slightly looser
+  // bound: measured 5-9 % faster end to end at k+1 = 6, 2-5 % at k+1 = 20), all 27 cells for longer lists, which the
+  // ~24 points of 8 cells cannot fill (tools/knn_seed_sweep.py)
+  const int near8 = g_seed_near8 == 1 ? 1 : g_seed_near8 == 2 ? 0 : (k1 <= 20);
   if (k1 <= 6)
     knn_seed_kernel<6><<<grid, 128, 0, stream>>>(sorted, N, G, params, csr.off, csr.list, thr0, near8);
   else if (k1 <= 20)
