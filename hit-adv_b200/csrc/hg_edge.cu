@@ -16,41 +16,55 @@
 
 namespace {
 
-// ---- forward: one CTA row per (b,c) plane, the plane's N source values staged in shared memory ------------------
+// ---- forward: a CTA pass covers kEdgeCP channels of one cloud: their N source values are staged in shared memory
+// and every index load (the expensive part: 8 B per edge, L2) serves kEdgeCP x 2 output rows ----------------------
+constexpr int kEdgeCP = 4;
 template <bool VEC4>
 __global__ void __launch_bounds__(256) edge_feature_kernel(const float *__restrict__ x,
                                                            const long long *__restrict__ idx, int C, int N, int k,
-                                                           long long planes, float *__restrict__ out) {
-  extern __shared__ float plane[];
+                                                           long long groups, float *__restrict__ out) {
+  extern __shared__ float plane[];  // [kEdgeCP][N]
   const int E = N * k;
-  for (long long bc = blockIdx.y; bc < planes; bc += gridDim.y) {
-    const long long b = bc / C;
-    const int c = (int)(bc % C);
-    const float *src = x + (size_t)bc * N;
+  const int gpc = (C + kEdgeCP - 1) / kEdgeCP;  // channel groups per cloud
+  for (long long gi = blockIdx.y; gi < groups; gi += gridDim.y) {
+    const long long b = gi / gpc;
+    const int c0 = (int)(gi % gpc) * kEdgeCP;
+    const int nc = min(kEdgeCP, C - c0);
     const long long *id = idx + (size_t)b * E;
-    float *dstA = out + ((size_t)b * 2 * C + c) * E;
+    __syncthreads();
+    for (int i = threadIdx.x; i < nc * N; i += 256) plane[i] = __ldg(x + ((size_t)b * C + c0) * N + i);
+    __syncthreads();
+    float *dstA = out + ((size_t)b * 2 * C + c0) * E;
     float *dstB = dstA + (size_t)C * E;
-    __syncthreads();
-    for (int i = threadIdx.x; i < N; i += 256) plane[i] = __ldg(src + i);
-    __syncthreads();
     if (VEC4) {  // k % 4 == 0: the four edges of a float4 share their centre point
       for (int e = (blockIdx.x * 256 + threadIdx.x) * 4; e < E; e += gridDim.x * 1024) {
         const longlong2 i01 = *reinterpret_cast<const longlong2 *>(id + e);
         const longlong2 i23 = *reinterpret_cast<const longlong2 *>(id + e + 2);
-        const float ctr = plane[e / k];
-        float4 a;
-        a.x = plane[i01.x] - ctr;
-        a.y = plane[i01.y] - ctr;
-        a.z = plane[i23.x] - ctr;
-        a.w = plane[i23.y] - ctr;
-        __stcs(reinterpret_cast<float4 *>(dstA + e), a);  // streaming: consumed by the next layer, not here
-        __stcs(reinterpret_cast<float4 *>(dstB + e), make_float4(ctr, ctr, ctr, ctr));
+        const int n = e / k;
+#pragma unroll
+        for (int q = 0; q < kEdgeCP; ++q) {
+          if (q < nc) {
+            const float *pl = plane + q * N;
+            const float ctr = pl[n];
+            float4 a;
+            a.x = pl[i01.x] - ctr;
+            a.y = pl[i01.y] - ctr;
+            a.z = pl[i23.x] - ctr;
+            a.w = pl[i23.y] - ctr;
+            __stcs(reinterpret_cast<float4 *>(dstA + (size_t)q * E + e), a);  // streaming: consumed by the next layer
+            __stcs(reinterpret_cast<float4 *>(dstB + (size_t)q * E + e), make_float4(ctr, ctr, ctr, ctr));
+          }
+        }
       }
     } else {
       for (int e = blockIdx.x * 256 + threadIdx.x; e < E; e += gridDim.x * 256) {
-        const float ctr = plane[e / k];
-        dstA[e] = plane[id[e]] - ctr;
-        dstB[e] = ctr;
+        const long long ii = id[e];
+        const int n = e / k;
+        for (int q = 0; q < nc; ++q) {
+          const float ctr = plane[q * N + n];
+          dstA[(size_t)q * E + e] = plane[q * N + ii] - ctr;
+          dstB[(size_t)q * E + e] = ctr;
+        }
       }
     }
   }
@@ -166,25 +180,28 @@ HG_API int hg_edge_feature_f32(const float *x, const int64_t *idx, int B, int C,
   HG_REQUIRE(x && idx && out, HG_E_BADARG, "edge_feature: null pointer");
   HG_REQUIRE(B > 0 && C > 0 && N > 0 && k > 0, HG_E_BADARG, "edge_feature: sizes must be positive");
   HG_REQUIRE((long long)N * k < (1LL << 31), HG_E_UNSUPPORTED, "edge_feature: N*k too large");
-  HG_REQUIRE((size_t)N * sizeof(float) <= 200 * 1024, HG_E_UNSUPPORTED, "edge_feature: N=%d too large for the staged plane", N);
-  const long long planes = (long long)B * C;
+  HG_REQUIRE((size_t)kEdgeCP * N * sizeof(float) <= 200 * 1024, HG_E_UNSUPPORTED,
+             "edge_feature: N=%d too large for the staged planes", N);
+  const long long groups = (long long)B * ((C + kEdgeCP - 1) / kEdgeCP);
   const int E = N * k;
   const bool vec = (k % 4 == 0) && ((reinterpret_cast<uintptr_t>(idx) | reinterpret_cast<uintptr_t>(out)) % 16 == 0);
   const int per_block = vec ? 1024 : 256;
   int gx = (E + per_block - 1) / per_block;
-  const int gx_cap = planes >= 4LL * hg_sm_count() ? 1 : 4;  // one CTA per plane once the planes fill the machine
+  // enough CTAs to fill the machine a few times over, each amortising its plane staging over >= 1/gx of the edges
+  int gx_cap = (int)((8LL * hg_sm_count() + groups - 1) / groups);
+  if (gx_cap < 1) gx_cap = 1;
   if (gx > gx_cap) gx = gx_cap;
-  const int gy = (int)(planes < 65535 ? planes : 65535);
-  const size_t smem = (size_t)N * sizeof(float);
+  const int gy = (int)(groups < 65535 ? groups : 65535);
+  const size_t smem = (size_t)kEdgeCP * N * sizeof(float);
   const bool prof = hg_prof_begin(HG_PROF_GROUP, stream);
   if (vec) {
     if (smem > 48 * 1024)
       HG_CUDA(cudaFuncSetAttribute(edge_feature_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    edge_feature_kernel<true><<<dim3(gx, gy), 256, smem, stream>>>(x, (const long long *)idx, C, N, k, planes, out);
+    edge_feature_kernel<true><<<dim3(gx, gy), 256, smem, stream>>>(x, (const long long *)idx, C, N, k, groups, out);
   } else {
     if (smem > 48 * 1024)
       HG_CUDA(cudaFuncSetAttribute(edge_feature_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    edge_feature_kernel<false><<<dim3(gx, gy), 256, smem, stream>>>(x, (const long long *)idx, C, N, k, planes, out);
+    edge_feature_kernel<false><<<dim3(gx, gy), 256, smem, stream>>>(x, (const long long *)idx, C, N, k, groups, out);
   }
   hg_prof_end(HG_PROF_GROUP, stream, prof);
   HG_CHECK_LAUNCH("edge_feature_kernel");

@@ -38,73 +38,80 @@ int ref_opt_n_threads(int work_size) {
 // four gathers that hit L1/L2 -- a plane of n floats is a few KB --, one float4 store), no integer division.
 // SMEM: the (b,c) source plane (n floats) is staged in shared memory first -- random 4-byte gathers from L1 cost one
 // wavefront per distinct line and cap the kernel near 2 TB/s; from shared memory they cost a few bank cycles.
+// A CTA pass covers kGatherCP channels of one cloud, so that every index load serves kGatherCP output rows.
+constexpr int kGatherCP = 4;
 template <bool VEC4, bool SMEM>
 __global__ void __launch_bounds__(256) gather_channel_major_kernel(const float *__restrict__ points,
                                                                    const int *__restrict__ idx, int c, int n, int E,
-                                                                   long long planes, float *__restrict__ out) {
-  extern __shared__ float plane[];
-  for (long long bc = blockIdx.y; bc < planes; bc += gridDim.y) {
-    const int bi = (int)(bc / c);
-    const float *src = points + (size_t)bc * n;
+                                                                   long long groups, float *__restrict__ out) {
+  extern __shared__ float plane[];  // SMEM: [kGatherCP][n]
+  const int gpc = (c + kGatherCP - 1) / kGatherCP;  // channel groups per cloud
+  for (long long gi = blockIdx.y; gi < groups; gi += gridDim.y) {
+    const long long bi = gi / gpc;
+    const int c0 = (int)(gi % gpc) * kGatherCP;
+    const int nc = min(kGatherCP, c - c0);
+    const float *src = points + ((size_t)bi * c + c0) * n;
     const int *id = idx + (size_t)bi * E;
-    float *dst = out + (size_t)bc * E;
+    float *dst = out + ((size_t)bi * c + c0) * E;
     if (SMEM) {
       __syncthreads();
-      for (int k = threadIdx.x; k < n; k += 256) plane[k] = __ldg(src + k);
+      for (int k = threadIdx.x; k < nc * n; k += 256) plane[k] = __ldg(src + k);
       __syncthreads();
     }
     const float *tab = SMEM ? plane : src;
     if (VEC4) {
       const int step = gridDim.x * 1024;
       int e = (blockIdx.x * 256 + threadIdx.x) * 4;
-      for (; e + 3 * step < E; e += 4 * step) {  // four index loads in flight per thread (memory-level parallelism)
-        int4 a[4];
+      for (; e + step < E; e += 2 * step) {  // two index loads in flight per thread
+        const int4 a0 = *reinterpret_cast<const int4 *>(id + e), a1 = *reinterpret_cast<const int4 *>(id + e + step);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) a[u] = *reinterpret_cast<const int4 *>(id + e + u * step);
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          float4 v;
-          v.x = tab[a[u].x];
-          v.y = tab[a[u].y];
-          v.z = tab[a[u].z];
-          v.w = tab[a[u].w];
-          __stcs(reinterpret_cast<float4 *>(dst + e + u * step), v);  // streaming store: not re-read here
-        }
+        for (int q = 0; q < kGatherCP; ++q)
+          if (q < nc) {
+            const float *t = tab + (size_t)q * n;
+            __stcs(reinterpret_cast<float4 *>(dst + (size_t)q * E + e), make_float4(t[a0.x], t[a0.y], t[a0.z], t[a0.w]));
+            __stcs(reinterpret_cast<float4 *>(dst + (size_t)q * E + e + step),
+                   make_float4(t[a1.x], t[a1.y], t[a1.z], t[a1.w]));
+          }
       }
       for (; e < E; e += step) {
         const int4 a = *reinterpret_cast<const int4 *>(id + e);
-        float4 v;
-        v.x = tab[a.x];
-        v.y = tab[a.y];
-        v.z = tab[a.z];
-        v.w = tab[a.w];
-        __stcs(reinterpret_cast<float4 *>(dst + e), v);
+#pragma unroll
+        for (int q = 0; q < kGatherCP; ++q)
+          if (q < nc) {
+            const float *t = tab + (size_t)q * n;
+            __stcs(reinterpret_cast<float4 *>(dst + (size_t)q * E + e), make_float4(t[a.x], t[a.y], t[a.z], t[a.w]));
+          }
       }
     } else {
-      for (int e = blockIdx.x * 256 + threadIdx.x; e < E; e += gridDim.x * 256) dst[e] = tab[__ldg(id + e)];
+      for (int e = blockIdx.x * 256 + threadIdx.x; e < E; e += gridDim.x * 256) {
+        const int a = __ldg(id + e);
+        for (int q = 0; q < nc; ++q) dst[(size_t)q * E + e] = tab[(size_t)q * n + a];
+      }
     }
   }
 }
 
 int launch_gather(const float *points, const int *idx, int b, int c, int n, int E, float *out, cudaStream_t stream,
                   int prof_tag) {
-  const long long planes = (long long)b * c;
+  const long long groups = (long long)b * ((c + kGatherCP - 1) / kGatherCP);
   const bool vec = (E % 4 == 0) && ((reinterpret_cast<uintptr_t>(idx) | reinterpret_cast<uintptr_t>(out)) % 16 == 0);
   const int per_block = vec ? 1024 : 256;
-  // stage the plane when it is re-used enough (E >= n) and fits; then one CTA column per plane
-  const bool use_smem = (size_t)n * sizeof(float) <= 96 * 1024 && E >= n;
+  // stage the planes when they are re-used enough (E >= n) and fit
+  const bool use_smem = (size_t)kGatherCP * n * sizeof(float) <= 96 * 1024 && E >= n;
   int gx = (E + per_block - 1) / per_block;
-  // staged plane: one CTA per plane when there are enough planes to fill the machine (amortises the staging)
-  const int gx_cap = use_smem ? (planes >= 4LL * hg_sm_count() ? 1 : 4) : 64;
-  if (gx > gx_cap) gx = gx_cap;
-  const int gy = (int)(planes < 65535 ? planes : 65535);
-  const size_t smem = use_smem ? (size_t)n * sizeof(float) : 0;
+  // enough CTAs to fill the machine a few times over; with staged planes each CTA amortises its staging over >= 1/gx
+  // of the indices
+  long long gx_cap = use_smem ? (8LL * hg_sm_count() + groups - 1) / groups : 64;
+  if (gx_cap < 1) gx_cap = 1;
+  if (gx > gx_cap) gx = (int)gx_cap;
+  const int gy = (int)(groups < 65535 ? groups : 65535);
+  const size_t smem = use_smem ? (size_t)kGatherCP * n * sizeof(float) : 0;
   const bool prof = prof_tag >= 0 ? hg_prof_begin(prof_tag, stream) : false;
 #define HG_GATHER_LAUNCH(V, S)                                                                                     \
   do {                                                                                                             \
     if (smem > 48 * 1024)                                                                                          \
       cudaFuncSetAttribute(gather_channel_major_kernel<V, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-    gather_channel_major_kernel<V, S><<<dim3(gx, gy), 256, smem, stream>>>(points, idx, c, n, E, planes, out);     \
+    gather_channel_major_kernel<V, S><<<dim3(gx, gy), 256, smem, stream>>>(points, idx, c, n, E, groups, out);     \
   } while (0)
   if (vec && use_smem) HG_GATHER_LAUNCH(true, true);
   else if (vec) HG_GATHER_LAUNCH(true, false);
