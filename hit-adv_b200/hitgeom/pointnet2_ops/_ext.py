@@ -1,6 +1,9 @@
 """`pointnet2_ops._ext` -- the nine functions the reference's pybind11 module exports
-(pointnet2_ops_lib/pointnet2_ops/_ext-src/src/bindings.cpp:6-19), same names, argument order, dtypes,
-shapes and zero-initialised outputs, implemented by handing raw pointers to libhitgeom.so.
+(pointnet2_ops_lib/pointnet2_ops/_ext-src/src/bindings.cpp:6-19), same names, argument order, dtypes and
+shapes, implemented by handing raw pointers to libhitgeom.so.  The reference allocates its outputs with
+`torch::zeros` because its kernels skip entries (an empty ball keeps its zeros, the atomicAdd gradients need a zero
+start); hitgeom's kernels write EVERY output element (same values, an empty ball is written as zeros), so the
+outputs are `torch.empty` -- the memset was up to 40 % of a group_points call.
 
 Host-side behaviour mirrored from the reference's .cpp wrappers (ball_query.cpp:8-32, group_points.cpp:12-62,
 sampling.cpp:15-87, interpolate.cpp:14-99): contiguity / dtype checks raise RuntimeError (the reference's
@@ -27,7 +30,7 @@ def gather_points(points, idx):
     require(idx, "idx", torch.int32, 2)
     B, C, N = points.shape
     M = idx.shape[1]
-    out = torch.zeros((B, C, M), dtype=torch.float32, device=points.device)
+    out = torch.empty((B, C, M), dtype=torch.float32, device=points.device)
     with torch.cuda.device(points.device):
         check(lib().hg_p2_gather_points(B, C, N, M, ptr(points), ptr(idx), ptr(out), stream_ptr()), "gather_points")
     return out
@@ -39,7 +42,7 @@ def gather_points_grad(grad_out, idx, n):
     require(grad_out, "grad_out", torch.float32, 3)
     require(idx, "idx", torch.int32, 2)
     B, C, M = grad_out.shape
-    out = torch.zeros((B, C, n), dtype=torch.float32, device=grad_out.device)
+    out = torch.empty((B, C, n), dtype=torch.float32, device=grad_out.device)
     with torch.cuda.device(grad_out.device):
         ws = workspace(lib().hg_p2_scatter_workspace_bytes(B, n, M), grad_out.device)
         check(lib().hg_p2_gather_points_grad(B, C, n, M, ptr(grad_out), ptr(idx), ptr(out), ptr(ws), ws.numel(),
@@ -52,7 +55,7 @@ def furthest_point_sampling(points, nsamples):
     _cuda_or_raise(points, "points")
     require(points, "points", torch.float32, 3)
     B, N, _ = points.shape
-    out = torch.zeros((B, nsamples), dtype=torch.int32, device=points.device)
+    out = torch.empty((B, nsamples), dtype=torch.int32, device=points.device)
     with torch.cuda.device(points.device):
         check(lib().hg_p2_furthest_point_sampling(B, N, nsamples, ptr(points), None, ptr(out), stream_ptr()),
               "furthest_point_sampling")
@@ -66,8 +69,8 @@ def three_nn(unknowns, knows):
     require(knows, "knows", torch.float32, 3)
     B, n, _ = unknowns.shape
     m = knows.shape[1]
-    idx = torch.zeros((B, n, 3), dtype=torch.int32, device=unknowns.device)
-    dist2 = torch.zeros((B, n, 3), dtype=torch.float32, device=unknowns.device)
+    idx = torch.empty((B, n, 3), dtype=torch.int32, device=unknowns.device)
+    dist2 = torch.empty((B, n, 3), dtype=torch.float32, device=unknowns.device)
     with torch.cuda.device(unknowns.device):
         check(lib().hg_p2_three_nn(B, n, m, ptr(unknowns), ptr(knows), ptr(dist2), ptr(idx), stream_ptr()), "three_nn")
     return [dist2, idx]
@@ -81,7 +84,7 @@ def three_interpolate(points, idx, weight):
     require(weight, "weight", torch.float32, 3)
     B, c, m = points.shape
     n = idx.shape[1]
-    out = torch.zeros((B, c, n), dtype=torch.float32, device=points.device)
+    out = torch.empty((B, c, n), dtype=torch.float32, device=points.device)
     with torch.cuda.device(points.device):
         check(lib().hg_p2_three_interpolate(B, c, m, n, ptr(points), ptr(idx), ptr(weight), ptr(out), stream_ptr()),
               "three_interpolate")
@@ -95,7 +98,7 @@ def three_interpolate_grad(grad_out, idx, weight, m):
     require(idx, "idx", torch.int32, 3)
     require(weight, "weight", torch.float32, 3)
     B, c, n = grad_out.shape
-    out = torch.zeros((B, c, m), dtype=torch.float32, device=grad_out.device)
+    out = torch.empty((B, c, m), dtype=torch.float32, device=grad_out.device)
     with torch.cuda.device(grad_out.device):
         ws = workspace(lib().hg_p2_scatter_workspace_bytes(B, m, n * 3), grad_out.device)
         check(lib().hg_p2_three_interpolate_grad(B, c, n, m, ptr(grad_out), ptr(idx), ptr(weight), ptr(out), ptr(ws),
@@ -110,7 +113,7 @@ def ball_query(new_xyz, xyz, radius, nsample):
     require(xyz, "xyz", torch.float32, 3)
     B, M, _ = new_xyz.shape
     N = xyz.shape[1]
-    idx = torch.zeros((B, M, nsample), dtype=torch.int32, device=new_xyz.device)
+    idx = torch.empty((B, M, nsample), dtype=torch.int32, device=new_xyz.device)
     with torch.cuda.device(new_xyz.device):
         check(lib().hg_p2_ball_query(B, N, M, float(radius), int(nsample), ptr(new_xyz), ptr(xyz), ptr(idx),
                                      stream_ptr()), "ball_query")
@@ -124,7 +127,7 @@ def group_points(points, idx):
     require(idx, "idx", torch.int32, 3)
     B, C, N = points.shape
     _, S, ns = idx.shape
-    out = torch.zeros((B, C, S, ns), dtype=torch.float32, device=points.device)
+    out = torch.empty((B, C, S, ns), dtype=torch.float32, device=points.device)
     with torch.cuda.device(points.device):
         check(lib().hg_p2_group_points(B, C, N, S, ns, ptr(points), ptr(idx), ptr(out), stream_ptr()), "group_points")
     return out
@@ -136,7 +139,7 @@ def group_points_grad(grad_out, idx, n):
     require(grad_out, "grad_out", torch.float32, 4)
     require(idx, "idx", torch.int32, 3)
     B, C, S, ns = grad_out.shape
-    out = torch.zeros((B, C, n), dtype=torch.float32, device=grad_out.device)
+    out = torch.empty((B, C, n), dtype=torch.float32, device=grad_out.device)
     with torch.cuda.device(grad_out.device):
         ws = workspace(lib().hg_p2_scatter_workspace_bytes(B, n, S * ns), grad_out.device)
         check(lib().hg_p2_group_points_grad(B, C, n, S, ns, ptr(grad_out), ptr(idx), ptr(out), ptr(ws), ws.numel(),
