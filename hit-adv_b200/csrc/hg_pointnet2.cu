@@ -151,6 +151,68 @@ __global__ void __launch_bounds__(256) scatter_channel_major_kernel(const float 
   }
 }
 
+// Staged variant for the gather / group gradients (DIV = 1, unweighted): one CTA per (b,c) plane copies the plane's E
+// source values into shared memory with coalesced float4 loads, then every thread sums its destination's incoming
+// edges from shared memory (the generic kernel above gathers 4 bytes per 32-byte sector from global memory).  Same
+// sequential summation order (ascending edge) => the same bits as the generic kernel and the oracle.
+constexpr int kScatterThreads = 256;
+__global__ void __launch_bounds__(kScatterThreads) scatter_staged_kernel(const float *__restrict__ src,
+                                                                         const int *__restrict__ off,
+                                                                         const int *__restrict__ list, int c, int n, int E,
+                                                                         long long planes, float *__restrict__ grad_points) {
+  extern __shared__ float sA[];  // [E]
+  for (long long bc = blockIdx.x; bc < planes; bc += gridDim.x) {
+    const long long bi = bc / c;
+    const float *s = src + (size_t)bc * E;
+    const int *o = off + (size_t)bi * (n + 1);
+    const int *l = list + (size_t)bi * E;
+    float *dst = grad_points + (size_t)bc * n;
+    __syncthreads();
+    if ((E & 3) == 0 && (reinterpret_cast<uintptr_t>(s) & 15) == 0) {
+      for (int e = threadIdx.x * 4; e < E; e += kScatterThreads * 4)
+        *reinterpret_cast<float4 *>(sA + e) = __ldcs(reinterpret_cast<const float4 *>(s + e));
+    } else {
+      for (int e = threadIdx.x; e < E; e += kScatterThreads) sA[e] = s[e];
+    }
+    __syncthreads();
+    for (int key = threadIdx.x; key < n; key += kScatterThreads) {
+      const int q1 = o[key + 1];
+      int q = o[key];
+      float acc = 0.f;
+      for (; q + 3 < q1; q += 4) {  // four list entries in flight
+        const int e0 = __ldg(l + q), e1 = __ldg(l + q + 1), e2 = __ldg(l + q + 2), e3 = __ldg(l + q + 3);
+        acc = __fadd_rn(acc, sA[e0]);
+        acc = __fadd_rn(acc, sA[e1]);
+        acc = __fadd_rn(acc, sA[e2]);
+        acc = __fadd_rn(acc, sA[e3]);
+      }
+      for (; q < q1; ++q) acc = __fadd_rn(acc, sA[__ldg(l + q)]);
+      dst[key] = acc;
+    }
+  }
+}
+
+// gradient of gather / group: staged kernel when the plane fits in shared memory, generic kernel otherwise
+int launch_scatter_unweighted(const float *grad_out, const HgCsr &csr, int b, int c, int n, int E, float *grad_points,
+                              cudaStream_t stream) {
+  const size_t smem = (size_t)E * sizeof(float);
+  if (smem <= 100 * 1024 && E >= n) {  // (two CTAs per SM)
+    if (smem > 48 * 1024)
+      HG_CUDA(cudaFuncSetAttribute(scatter_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long planes = (long long)b * c;
+    long long grid = planes;
+    const long long cap = (long long)hg_sm_count() * 8;
+    if (grid > cap) grid = cap;
+    scatter_staged_kernel<<<(int)grid, kScatterThreads, smem, stream>>>(grad_out, csr.off, csr.list, c, n, E, planes,
+                                                                       grad_points);
+  } else {
+    const long long total = (long long)b * c * n;
+    scatter_channel_major_kernel<1, false><<<grid_for(total, 256), 256, 0, stream>>>(grad_out, nullptr, csr.off, csr.list,
+                                                                                     b, c, n, E, grad_points);
+  }
+  return HG_OK;
+}
+
 // ---- ball query (ball_query_gpu.cu:9-44) -------------------------------------------------------------------
 __global__ void __launch_bounds__(128) ball_query_kernel(int n, int m, float radius2, int nsample,
                                                          const float *__restrict__ new_xyz,
@@ -407,9 +469,8 @@ HG_API int hg_p2_gather_points_grad(int b, int c, int n, int npoints, const floa
   HgCsr csr;
   int rc = hg_csr_build(idx, b, npoints, n, workspace, workspace_bytes, &csr, stream);
   if (rc) return rc;
-  const long long total = (long long)b * c * n;
-  scatter_channel_major_kernel<1, false><<<grid_for(total, 256), 256, 0, stream>>>(grad_out, nullptr, csr.off, csr.list,
-                                                                                   b, c, n, npoints, grad_points);
+  rc = launch_scatter_unweighted(grad_out, csr, b, c, n, npoints, grad_points, stream);
+  if (rc) return rc;
   HG_CHECK_LAUNCH("gather_points_grad");
   return HG_OK;
 }
@@ -461,9 +522,8 @@ HG_API int hg_p2_group_points_grad(int b, int c, int n, int npoints, int nsample
   HgCsr csr;
   int rc = hg_csr_build(idx, b, E, n, workspace, workspace_bytes, &csr, stream);
   if (rc) return rc;
-  const long long total = (long long)b * c * n;
-  scatter_channel_major_kernel<1, false><<<grid_for(total, 256), 256, 0, stream>>>(grad_out, nullptr, csr.off, csr.list,
-                                                                                   b, c, n, E, grad_points);
+  rc = launch_scatter_unweighted(grad_out, csr, b, c, n, E, grad_points, stream);
+  if (rc) return rc;
   HG_CHECK_LAUNCH("group_points_grad");
   return HG_OK;
 }
