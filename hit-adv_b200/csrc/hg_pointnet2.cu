@@ -316,6 +316,39 @@ __global__ void __launch_bounds__(256) three_interpolate_kernel(int b, int c, in
   }
 }
 
+// Staged variant: a CTA pass covers kInterpCP channels of one cloud (their m source values in shared memory), so the
+// three (index, weight) pairs of an output position are loaded once for kInterpCP output rows, and the gathers hit
+// shared memory.  Same arithmetic.
+constexpr int kInterpCP = 8;
+__global__ void __launch_bounds__(256) three_interpolate_staged_kernel(int c, int m, int n, long long groups,
+                                                                       const float *__restrict__ points,
+                                                                       const int *__restrict__ idx,
+                                                                       const float *__restrict__ weight,
+                                                                       float *__restrict__ out) {
+  extern __shared__ float plane[];  // [kInterpCP][m]
+  const int gpc = (c + kInterpCP - 1) / kInterpCP;
+  for (long long gi = blockIdx.y; gi < groups; gi += gridDim.y) {
+    const long long bi = gi / gpc;
+    const int c0 = (int)(gi % gpc) * kInterpCP;
+    const int nc = min(kInterpCP, c - c0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < nc * m; i += 256) plane[i] = __ldg(points + ((size_t)bi * c + c0) * m + i);
+    __syncthreads();
+    for (int j = blockIdx.x * 256 + threadIdx.x; j < n; j += gridDim.x * 256) {
+      const int *id = idx + ((size_t)bi * n + j) * 3;
+      const float *w = weight + ((size_t)bi * n + j) * 3;
+      const int i0 = id[0], i1 = id[1], i2 = id[2];
+      const float w0 = w[0], w1 = w[1], w2 = w[2];
+#pragma unroll
+      for (int q = 0; q < kInterpCP; ++q)
+        if (q < nc) {
+          const float *p = plane + q * m;
+          out[((size_t)bi * c + c0 + q) * n + j] = __fmaf_rn(p[i2], w2, __fmaf_rn(p[i0], w0, __fmul_rn(p[i1], w1)));
+        }
+    }
+  }
+}
+
 // ---- furthest point sampling ---------------------------------------------------------------------------------
 // POLICY_P2   : sampling_gpu.cu:69-173.  d = fma(dz,dz,fma(dx,dx,dy*dy)); points with |p|^2 <= 1e-3 are skipped;
 //               start index 0; ties resolved like the reference's shared-memory tree: smallest
@@ -542,8 +575,21 @@ HG_API int hg_p2_three_interpolate(int b, int c, int m, int n, const float *poin
                                    const float *weight, float *out, hgStream stream_) {
   HG_REQUIRE(points && idx && weight && out, HG_E_BADARG, "three_interpolate: null pointer");
   HG_REQUIRE(b > 0 && c > 0 && m > 0 && n > 0, HG_E_BADARG, "three_interpolate: sizes must be positive");
-  const long long total = (long long)b * c * n;
-  three_interpolate_kernel<<<grid_for(total, 256), 256, 0, hg_stream(stream_)>>>(b, c, m, n, points, idx, weight, out);
+  const size_t smem = (size_t)kInterpCP * m * sizeof(float);
+  if (smem <= 96 * 1024) {
+    if (smem > 48 * 1024)
+      HG_CUDA(cudaFuncSetAttribute(three_interpolate_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long groups = (long long)b * ((c + kInterpCP - 1) / kInterpCP);
+    int gx = (n + 255) / 256;
+    long long gx_cap = (8LL * hg_sm_count() + groups - 1) / groups;
+    if (gx_cap < 1) gx_cap = 1;
+    if (gx > gx_cap) gx = (int)gx_cap;
+    three_interpolate_staged_kernel<<<dim3(gx, (unsigned)(groups < 65535 ? groups : 65535)), 256, smem, hg_stream(stream_)>>>(
+        c, m, n, groups, points, idx, weight, out);
+  } else {
+    const long long total = (long long)b * c * n;
+    three_interpolate_kernel<<<grid_for(total, 256), 256, 0, hg_stream(stream_)>>>(b, c, m, n, points, idx, weight, out);
+  }
   HG_CHECK_LAUNCH("three_interpolate");
   return HG_OK;
 }
