@@ -90,9 +90,10 @@ __global__ void __launch_bounds__(kCsrThreads) csr_build_kernel(const int *__res
 
 }  // namespace
 
-// Small problems (few edges per cloud) are launch-bound: one stable single-kernel build beats memset + count + scan
-// + fill.  hg_csr_build_unordered switches on this and the workspace formula follows it.
-static inline bool csr_small(int E) { return E <= 16384; }
+// Tiny problems (a couple of thousand edges per cloud) are launch-bound: one stable single-kernel build beats memset +
+// count + scan + fill.  Beyond that the single CTA per cloud of the stable builder is the bottleneck (48 us against
+// ~20 us for 388 clouds x 6144 edges).  hg_csr_build_unordered switches on this and the workspace formula follows it.
+static inline bool csr_small(int E) { return E <= 2048; }
 
 size_t hg_csr_workspace_bytes(int B, int N, int E) {
   const size_t cursors = csr_small(E) ? (size_t)kCsrWarps * N : (size_t)N;
