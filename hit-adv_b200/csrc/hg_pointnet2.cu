@@ -43,7 +43,8 @@ constexpr int kGatherCP = 4;
 template <bool VEC4, bool SMEM>
 __global__ void __launch_bounds__(256) gather_channel_major_kernel(const float *__restrict__ points,
                                                                    const int *__restrict__ idx, int c, int n, int E,
-                                                                   long long groups, float *__restrict__ out) {
+                                                                   long long groups, float *__restrict__ out,
+                                                                   int oc_total, int oc_off) {
   extern __shared__ float plane[];  // SMEM: [kGatherCP][n]
   const int gpc = (c + kGatherCP - 1) / kGatherCP;  // channel groups per cloud
   for (long long gi = blockIdx.y; gi < groups; gi += gridDim.y) {
@@ -52,7 +53,7 @@ __global__ void __launch_bounds__(256) gather_channel_major_kernel(const float *
     const int nc = min(kGatherCP, c - c0);
     const float *src = points + ((size_t)bi * c + c0) * n;
     const int *id = idx + (size_t)bi * E;
-    float *dst = out + ((size_t)bi * c + c0) * E;
+    float *dst = out + ((size_t)bi * oc_total + oc_off + c0) * E;  // (oc_total, oc_off): a channel slice of a wider output
     if (SMEM) {
       __syncthreads();
       for (int k = threadIdx.x; k < nc * n; k += 256) plane[k] = __ldg(src + k);
@@ -92,7 +93,8 @@ __global__ void __launch_bounds__(256) gather_channel_major_kernel(const float *
 }
 
 int launch_gather(const float *points, const int *idx, int b, int c, int n, int E, float *out, cudaStream_t stream,
-                  int prof_tag) {
+                  int prof_tag, int oc_total = 0, int oc_off = 0) {
+  if (oc_total == 0) oc_total = c;
   const long long groups = (long long)b * ((c + kGatherCP - 1) / kGatherCP);
   const bool vec = (E % 4 == 0) && ((reinterpret_cast<uintptr_t>(idx) | reinterpret_cast<uintptr_t>(out)) % 16 == 0);
   const int per_block = vec ? 1024 : 256;
@@ -111,7 +113,8 @@ int launch_gather(const float *points, const int *idx, int b, int c, int n, int 
   do {                                                                                                             \
     if (smem > 48 * 1024)                                                                                          \
       cudaFuncSetAttribute(gather_channel_major_kernel<V, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-    gather_channel_major_kernel<V, S><<<dim3(gx, gy), 256, smem, stream>>>(points, idx, c, n, E, groups, out);     \
+    gather_channel_major_kernel<V, S><<<dim3(gx, gy), 256, smem, stream>>>(points, idx, c, n, E, groups, out,      \
+                                                                           oc_total, oc_off);                      \
   } while (0)
   if (vec && use_smem) HG_GATHER_LAUNCH(true, true);
   else if (vec) HG_GATHER_LAUNCH(true, false);
@@ -129,9 +132,11 @@ __global__ void __launch_bounds__(256) scatter_channel_major_kernel(const float 
                                                                     const float *__restrict__ w,
                                                                     const int *__restrict__ off,
                                                                     const int *__restrict__ list, int b, int c, int n,
-                                                                    int E, float *__restrict__ grad_points) {
+                                                                    int E, float *__restrict__ grad_points,
+                                                                    int sc_total = 0, int sc_off = 0) {
   const long long total = (long long)b * c * n;
   const int Esrc = E / DIV;
+  if (sc_total == 0) sc_total = c;
   for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total;
        g += (long long)gridDim.x * blockDim.x) {
     const int key = (int)(g % n);
@@ -139,7 +144,7 @@ __global__ void __launch_bounds__(256) scatter_channel_major_kernel(const float 
     const int bi = (int)(bc / c);
     const int *o = off + (size_t)bi * (n + 1);
     const int *l = list + (size_t)bi * E;
-    const float *s = src + (size_t)bc * Esrc;
+    const float *s = src + ((size_t)bi * sc_total + sc_off + (int)(bc % c)) * Esrc;
     float acc = 0.f;
     for (int q = o[key]; q < o[key + 1]; ++q) {
       const int e = l[q];
@@ -159,11 +164,12 @@ constexpr int kScatterThreads = 256;
 __global__ void __launch_bounds__(kScatterThreads) scatter_staged_kernel(const float *__restrict__ src,
                                                                          const int *__restrict__ off,
                                                                          const int *__restrict__ list, int c, int n, int E,
-                                                                         long long planes, float *__restrict__ grad_points) {
+                                                                         long long planes, float *__restrict__ grad_points,
+                                                                         int sc_total, int sc_off) {
   extern __shared__ float sA[];  // [E]
   for (long long bc = blockIdx.x; bc < planes; bc += gridDim.x) {
     const long long bi = bc / c;
-    const float *s = src + (size_t)bc * E;
+    const float *s = src + ((size_t)bi * sc_total + sc_off + (int)(bc % c)) * E;  // a channel slice of a wider source
     const int *o = off + (size_t)bi * (n + 1);
     const int *l = list + (size_t)bi * E;
     float *dst = grad_points + (size_t)bc * n;
@@ -194,7 +200,8 @@ __global__ void __launch_bounds__(kScatterThreads) scatter_staged_kernel(const f
 
 // gradient of gather / group: staged kernel when the plane fits in shared memory, generic kernel otherwise
 int launch_scatter_unweighted(const float *grad_out, const HgCsr &csr, int b, int c, int n, int E, float *grad_points,
-                              cudaStream_t stream) {
+                              cudaStream_t stream, int sc_total = 0, int sc_off = 0) {
+  if (sc_total == 0) sc_total = c;
   const size_t smem = (size_t)E * sizeof(float);
   if (smem <= 100 * 1024 && E >= n) {  // (two CTAs per SM)
     if (smem > 48 * 1024)
@@ -204,13 +211,35 @@ int launch_scatter_unweighted(const float *grad_out, const HgCsr &csr, int b, in
     const long long cap = (long long)hg_sm_count() * 8;
     if (grid > cap) grid = cap;
     scatter_staged_kernel<<<(int)grid, kScatterThreads, smem, stream>>>(grad_out, csr.off, csr.list, c, n, E, planes,
-                                                                       grad_points);
+                                                                       grad_points, sc_total, sc_off);
   } else {
     const long long total = (long long)b * c * n;
     scatter_channel_major_kernel<1, false><<<grid_for(total, 256), 256, 0, stream>>>(grad_out, nullptr, csr.off, csr.list,
-                                                                                     b, c, n, E, grad_points);
+                                                                                     b, c, n, E, grad_points, sc_total,
+                                                                                     sc_off);
   }
   return HG_OK;
+}
+
+// QueryAndGroup's coordinate rows: out[b, d, s, t] = xyz[b, idx[b,s,t], d] - new_xyz[b, s, d], d < 3, written into the
+// first three channels of the (b, oc_total, S, ns) output
+__global__ void __launch_bounds__(256) group_xyz_rel_kernel(const float *__restrict__ xyz,
+                                                            const float *__restrict__ new_xyz,
+                                                            const int *__restrict__ idx, int n, int S, int ns,
+                                                            int oc_total, long long total, float *__restrict__ out) {
+  const int E = S * ns;
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total;
+       g += (long long)gridDim.x * blockDim.x) {
+    const long long bi = g / E;
+    const int e = (int)(g % E), sidx = e / ns;
+    const int a = __ldg(idx + g);
+    const float *p = xyz + ((size_t)bi * n + a) * 3;
+    const float *q = new_xyz + ((size_t)bi * S + sidx) * 3;
+    float *o = out + (size_t)bi * oc_total * E + e;
+    o[0] = __fsub_rn(__ldg(p), __ldg(q));
+    o[(size_t)E] = __fsub_rn(__ldg(p + 1), __ldg(q + 1));
+    o[(size_t)2 * E] = __fsub_rn(__ldg(p + 2), __ldg(q + 2));
+  }
 }
 
 // ---- ball query (ball_query_gpu.cu:9-44) -------------------------------------------------------------------
@@ -542,6 +571,47 @@ HG_API int hg_p2_group_points(int b, int c, int n, int npoints, int nsample, con
   HG_REQUIRE(points && idx && out, HG_E_BADARG, "group_points: null pointer");
   HG_REQUIRE(b > 0 && c > 0 && n > 0 && npoints > 0 && nsample > 0, HG_E_BADARG, "group_points: sizes must be positive");
   return launch_gather(points, idx, b, c, n, npoints * nsample, out, hg_stream(stream_), HG_PROF_GROUP);
+}
+
+// pointnet2_utils.py:279-333 QueryAndGroup.forward after its ball query, written once: rows 0..2 = grouped_xyz -
+// new_xyz, rows 3.. = grouped features (the reference: two grouping ops, an in-place subtraction and a torch.cat)
+HG_API int hg_p2_group_concat(int b, int c, int n, int npoints, int nsample, const float *xyz, const float *new_xyz,
+                              const float *features, const int *idx, float *out, hgStream stream_) {
+  cudaStream_t stream = hg_stream(stream_);
+  HG_REQUIRE(xyz && new_xyz && idx && out, HG_E_BADARG, "group_concat: null pointer");
+  HG_REQUIRE(b > 0 && c >= 0 && n > 0 && npoints > 0 && nsample > 0, HG_E_BADARG, "group_concat: bad sizes");
+  HG_REQUIRE(c == 0 || features, HG_E_BADARG, "group_concat: features is null but c > 0");
+  const long long total = (long long)b * npoints * nsample;
+  group_xyz_rel_kernel<<<grid_for(total, 256), 256, 0, stream>>>(xyz, new_xyz, idx, n, npoints, nsample, 3 + c, total,
+                                                                 out);
+  HG_CHECK_LAUNCH("group_xyz_rel_kernel");
+  if (c > 0) return launch_gather(features, idx, b, c, n, npoints * nsample, out, stream, HG_PROF_GROUP, 3 + c, 3);
+  return HG_OK;
+}
+
+// backward of hg_p2_group_concat w.r.t. the features (b,c,n) and the coordinates (as (b,3,n), channel-major); either
+// output may be NULL.  (d/d new_xyz is minus the sum over the samples of rows 0..2: a plain reduction, left to the host.)
+HG_API int hg_p2_group_concat_grad(int b, int c, int n, int npoints, int nsample, const float *grad_out, const int *idx,
+                                   float *grad_xyz_t, float *grad_features, void *workspace, size_t workspace_bytes,
+                                   hgStream stream_) {
+  cudaStream_t stream = hg_stream(stream_);
+  HG_REQUIRE(grad_out && idx && (grad_xyz_t || grad_features), HG_E_BADARG, "group_concat_grad: null pointer");
+  HG_REQUIRE(b > 0 && c >= 0 && n > 0 && npoints > 0 && nsample > 0, HG_E_BADARG, "group_concat_grad: bad sizes");
+  const int E = npoints * nsample;
+  HgCsr csr;
+  int rc = hg_csr_build(idx, b, E, n, workspace, workspace_bytes, &csr, stream);
+  if (rc) return rc;
+  if (grad_xyz_t) {
+    rc = launch_scatter_unweighted(grad_out, csr, b, 3, n, E, grad_xyz_t, stream, 3 + c, 0);
+    if (rc) return rc;
+    HG_CHECK_LAUNCH("group_concat_grad(xyz)");
+  }
+  if (grad_features && c > 0) {
+    rc = launch_scatter_unweighted(grad_out, csr, b, c, n, E, grad_features, stream, 3 + c, 3);
+    if (rc) return rc;
+    HG_CHECK_LAUNCH("group_concat_grad(features)");
+  }
+  return HG_OK;
 }
 
 HG_API int hg_p2_group_points_grad(int b, int c, int n, int npoints, int nsample, const float *grad_out,

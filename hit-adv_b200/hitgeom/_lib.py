@@ -59,6 +59,8 @@ _SIGNATURES = {
     "hg_p2_ball_query": (I, [I, I, I, F, I, P, P, P, P]),
     "hg_p2_group_points": (I, [I, I, I, I, I, P, P, P, P]),
     "hg_p2_group_points_grad": (I, [I, I, I, I, I, P, P, P, P, Z, P]),
+    "hg_p2_group_concat": (I, [I, I, I, I, I, P, P, P, P, P, P]),
+    "hg_p2_group_concat_grad": (I, [I, I, I, I, I, P, P, P, P, P, Z, P]),
     "hg_p2_three_nn": (I, [I, I, I, P, P, P, P, P]),
     "hg_p2_three_interpolate": (I, [I, I, I, I, P, P, P, P, P]),
     "hg_p2_three_interpolate_grad": (I, [I, I, I, I, P, P, P, P, P, Z, P]),

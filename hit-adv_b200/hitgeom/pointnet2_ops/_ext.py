@@ -145,3 +145,42 @@ def group_points_grad(grad_out, idx, n):
         check(lib().hg_p2_group_points_grad(B, C, n, S, ns, ptr(grad_out), ptr(idx), ptr(out), ptr(ws), ws.numel(),
                                             stream_ptr()), "group_points_grad")
     return out
+
+
+def group_concat(xyz, new_xyz, features, idx):
+    """hitgeom extension (no counterpart in bindings.cpp): the body of QueryAndGroup.forward after its ball query
+    (pointnet2_utils.py:312-333) in one pass.  xyz (B,N,3), new_xyz (B,S,3), features (B,C,N) or None, idx (B,S,ns) i32
+    -> (B,3+C,S,ns): rows 0..2 = xyz[idx] - new_xyz, rows 3.. = features[idx]."""
+    _cuda_or_raise(xyz, "xyz")
+    require(xyz, "xyz", torch.float32, 3)
+    require(new_xyz, "new_xyz", torch.float32, 3)
+    require(idx, "idx", torch.int32, 3)
+    B, N, _ = xyz.shape
+    _, S, ns = idx.shape
+    C = 0
+    if features is not None:
+        require(features, "features", torch.float32, 3)
+        C = features.shape[1]
+    out = torch.empty((B, 3 + C, S, ns), dtype=torch.float32, device=xyz.device)
+    with torch.cuda.device(xyz.device):
+        check(lib().hg_p2_group_concat(B, C, N, S, ns, ptr(xyz), ptr(new_xyz), ptr(features), ptr(idx), ptr(out),
+                                       stream_ptr()), "group_concat")
+    return out
+
+
+def group_concat_grad(grad_out, idx, n, want_xyz, want_features):
+    """grad_out (B,3+C,S,ns) -> (d/d xyz as (B,3,n) or None, d/d features (B,C,n) or None)."""
+    _cuda_or_raise(grad_out, "grad_out")
+    require(grad_out, "grad_out", torch.float32, 4)
+    require(idx, "idx", torch.int32, 3)
+    B, C3, S, ns = grad_out.shape
+    C = C3 - 3
+    gx = torch.empty((B, 3, n), dtype=torch.float32, device=grad_out.device) if want_xyz else None
+    gf = torch.empty((B, C, n), dtype=torch.float32, device=grad_out.device) if (want_features and C > 0) else None
+    if gx is None and gf is None:
+        return None, None
+    with torch.cuda.device(grad_out.device):
+        ws = workspace(lib().hg_p2_scatter_workspace_bytes(B, n, S * ns), grad_out.device)
+        check(lib().hg_p2_group_concat_grad(B, C, n, S, ns, ptr(grad_out), ptr(idx), ptr(gx), ptr(gf), ptr(ws), ws.numel(),
+                                            stream_ptr()), "group_concat_grad")
+    return gx, gf

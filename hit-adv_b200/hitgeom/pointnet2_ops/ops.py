@@ -74,8 +74,31 @@ grouping_operation = GroupingOperation.apply
 ball_query = BallQuery.apply
 
 
+class GroupConcat(Function):
+    """(xyz (B,N,3), new_xyz (B,S,3), features (B,C,N) | None, idx) -> (B,3+C,S,ns) = cat(xyz[idx] - new_xyz, features[idx])
+    in one pass; differentiable in xyz, new_xyz and features like the reference's composition."""
+
+    @staticmethod
+    def forward(ctx, xyz, new_xyz, features, idx):
+        ctx.n = xyz.size(1)
+        ctx.save_for_backward(idx)
+        return _ext.group_concat(xyz.contiguous(), new_xyz.contiguous(),
+                                 None if features is None else features.contiguous(), idx)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (idx,) = ctx.saved_tensors
+        need_xyz, need_new, need_f = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+        g = grad_out.contiguous()
+        gx_t, gf = _ext.group_concat_grad(g, idx, ctx.n, need_xyz, need_f)
+        gx = gx_t.transpose(1, 2).contiguous() if gx_t is not None else None
+        gn = -g[:, :3].sum(dim=3).transpose(1, 2).contiguous() if need_new else None
+        return gx, gn, gf, None
+
+
 class QueryAndGroup(nn.Module):
-    """ball_query -> grouping_operation -> subtract the centre -> optional concat with grouped features."""
+    """ball_query -> group the coordinates and subtract the centre -> optional concat with grouped features
+    (pointnet2_utils.py:279-333); with `use_xyz` the whole body after the ball query is one fused pass."""
 
     def __init__(self, radius, nsample, use_xyz=True):
         super().__init__()
@@ -83,13 +106,12 @@ class QueryAndGroup(nn.Module):
 
     def forward(self, xyz, new_xyz, features=None):
         idx = ball_query(self.radius, self.nsample, xyz, new_xyz)
-        rel = grouping_operation(xyz.transpose(1, 2).contiguous(), idx)  # (B,3,npoint,nsample)
-        rel -= new_xyz.transpose(1, 2).unsqueeze(-1)
         if features is None:
             assert self.use_xyz, "Cannot have not features and not use xyz as a feature!"
-            return rel
-        grouped = grouping_operation(features, idx)
-        return torch.cat([rel, grouped], dim=1) if self.use_xyz else grouped
+            return GroupConcat.apply(xyz, new_xyz, None, idx)
+        if self.use_xyz:
+            return GroupConcat.apply(xyz, new_xyz, features, idx)
+        return grouping_operation(features, idx)
 
 
 class GroupAll(nn.Module):

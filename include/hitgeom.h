@@ -155,6 +155,16 @@ int hg_p2_group_points(int b, int c, int n, int npoints, int nsample, const floa
 /* group_points.cpp:8-10 group_points_grad_kernel_wrapper */
 int hg_p2_group_points_grad(int b, int c, int n, int npoints, int nsample, const float *grad_out, const int *idx,
                             float *grad_points, void *workspace, size_t workspace_bytes, hgStream stream);
+/* pointnet2_utils.py:279-333 QueryAndGroup.forward after its ball query, fused: out (b, 3+c, npoints, nsample) with
+ * rows 0..2 = xyz[idx] - new_xyz and rows 3.. = features[idx] (the reference: two grouping ops, an in-place
+ * subtraction and a torch.cat over the full tensor).  xyz (b,n,3), new_xyz (b,npoints,3), features (b,c,n) or NULL
+ * with c = 0.  The gradient entry point returns d/d features (b,c,n) and d/d xyz as (b,3,n); either may be NULL;
+ * workspace as for group_points_grad (hg_p2_scatter_workspace_bytes(b, n, npoints*nsample)). */
+int hg_p2_group_concat(int b, int c, int n, int npoints, int nsample, const float *xyz, const float *new_xyz,
+                       const float *features, const int *idx, float *out, hgStream stream);
+int hg_p2_group_concat_grad(int b, int c, int n, int npoints, int nsample, const float *grad_out, const int *idx,
+                            float *grad_xyz_t, float *grad_features, void *workspace, size_t workspace_bytes,
+                            hgStream stream);
 /* interpolate.cpp:4-5 three_nn_kernel_wrapper  unknown(b,n,3) known(b,m,3) -> dist2(b,n,3) idx(b,n,3) */
 int hg_p2_three_nn(int b, int n, int m, const float *unknown, const float *known, float *dist2, int *idx,
                    hgStream stream);

@@ -74,3 +74,38 @@ def test_fp_module_without_known_broadcasts():
     m = pm.PointnetFPModule([6, 8]).cuda().eval()
     out = m(torch.randn(2, 50, 3).cuda(), None, None, torch.randn(2, 6, 1).cuda())
     assert out.shape == (2, 8, 50)
+
+
+@pytest.mark.parametrize("C", [0, 5, 64])
+def test_fused_group_concat_equals_the_composition(C):
+    """QueryAndGroup's fused body (hg_p2_group_concat) == two grouping ops + centre subtraction + cat: forward bit for bit,
+    gradients w.r.t. xyz / new_xyz / features as well (same deterministic ascending-edge sums)."""
+    from hitgeom.pointnet2_ops import pointnet2_utils as pu
+    from util_inputs import clouds
+
+    B, N, S, ns = 3, 500, 40, 16
+    xyz = torch.from_numpy(clouds(B, N, 61, "surface")).cuda()
+    new_xyz = xyz[:, :S].contiguous() + 0.01
+    feats = torch.randn(B, C, N, device="cuda") if C else None
+    idx = pu.ball_query(0.25, ns, xyz, new_xyz)
+    leaves = []
+    outs = []
+    for fused in (True, False):
+        x, nx = xyz.clone().requires_grad_(), new_xyz.clone().requires_grad_()
+        f = feats.clone().requires_grad_() if C else None
+        if fused:
+            out = pu.GroupConcat.apply(x, nx, f, idx)
+        else:
+            rel = pu.grouping_operation(x.transpose(1, 2).contiguous(), idx) - nx.transpose(1, 2).unsqueeze(-1)
+            out = torch.cat([rel, pu.grouping_operation(f, idx)], dim=1) if C else rel
+        outs.append(out)
+        leaves.append((x, nx, f))
+    assert torch.equal(outs[0], outs[1])
+    w = torch.randn_like(outs[0])
+    for out in outs:
+        (out * w).sum().backward()
+    (x0, n0, f0), (x1, n1, f1) = leaves
+    assert torch.equal(x0.grad, x1.grad)
+    assert normwise(n0.grad.cpu().numpy(), n1.grad.cpu().numpy()) < 1e-6  # (a reduction over the samples: order may differ)
+    if C:
+        assert torch.equal(f0.grad, f1.grad)
