@@ -121,6 +121,20 @@ def main():
         t_new = timeit(lambda: _ext.group_points_grad(go, idx, n), flush=flush)
         t_ref = timeit(lambda: ref.group_points_grad(go, idx, n), flush=flush) if ref else None
         row(f"group_points_grad B={B} C={C} n={n} S={S} ns={ns}", t_new, t_ref, bytes_alg=by + 4 * B * C * n)
+    # QueryAndGroup's body after the ball query (set-abstraction level 2 shape): fused pass vs the composition
+    from hitgeom.pointnet2_ops import pointnet2_utils as pu
+
+    xyz2 = new_xyz  # (B,512,3)
+    nx2 = new_xyz[:, :128].contiguous()
+    f2 = torch.randn(B, 128, 512, device="cuda")
+    idx2 = pu.ball_query(0.4, 64, xyz2, nx2)
+
+    def composed():
+        rel = pu.grouping_operation(xyz2.transpose(1, 2).contiguous(), idx2) - nx2.transpose(1, 2).unsqueeze(-1)
+        return torch.cat([rel, pu.grouping_operation(f2, idx2)], dim=1)
+
+    row("QueryAndGroup body B=64 C=128 n=512 S=128 ns=64 (fused group_concat)", timeit(lambda: pu.GroupConcat.apply(xyz2, nx2, f2, idx2), flush=flush),
+        timeit(composed, flush=flush), bytes_alg=4 * B * 131 * 128 * 64, extra={"ref": "hitgeom's own group kernels + subtraction + torch.cat (the reference's composition)"})
     unknown, known = xyz, new_xyz[:, :128].contiguous()
     t_new = timeit(lambda: _ext.three_nn(unknown, known))
     t_ref = timeit(lambda: ref.three_nn(unknown, known)) if ref else None
