@@ -304,6 +304,29 @@ __global__ void __launch_bounds__(256) knn_outlier_bwd_kernel(const float *__res
     const int *o = off + (size_t)b * (K + 1);
     const int *l = list + (size_t)b * K * k1;
     const int p0 = o[n], p1 = o[n + 1];
+    if (C == 3) {  // the hot case: walk the neighbour list and the reverse map ONCE for the three coordinates
+      const float v0 = p[(size_t)n * 3], v1 = p[(size_t)n * 3 + 1], v2 = p[(size_t)n * 3 + 2];
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+      if (own)
+        for (int t = 1; t < k1; ++t) {
+          const float *r = p + (size_t)nb[t] * 3;
+          a0 += 2.0f * (v0 - r[0]);
+          a1 += 2.0f * (v1 - r[1]);
+          a2 += 2.0f * (v2 - r[2]);
+        }
+      int e = -1;
+      for (int q = p0; q < p1; ++q) {  // ascending edge order, whatever order the list was filled in
+        e = hg_csr_next(l, p0, p1, e);
+        const float *r = p + (size_t)(e / k1) * 3;
+        a0 += 2.0f * (v0 - r[0]);
+        a1 += 2.0f * (v1 - r[1]);
+        a2 += 2.0f * (v2 - r[2]);
+      }
+      grad[(size_t)gi * 3] = coef * a0;
+      grad[(size_t)gi * 3 + 1] = coef * a1;
+      grad[(size_t)gi * 3 + 2] = coef * a2;
+      continue;
+    }
     for (int c = 0; c < C; ++c) {
       const float v = p[(size_t)n * C + c];
       float acc = 0.f;
