@@ -36,11 +36,11 @@ __global__ void knn_sumsq_kernel(const float *__restrict__ pc, long long total, 
   }
 }
 
-// dist tile: 128 rows x 64 columns per CTA, 8 x 4 per thread (columns as two packed pairs), channels consumed strictly
+// dist tile: 128 rows x 128 columns per CTA, 8 x 8 per thread (columns as four packed pairs), channels consumed strictly
 // in order: every accumulator is the reference's sequential FMA chain (product of channel 0 first, then c = 1..C-1).
-// Per channel a thread reads 8 row values (two broadcast LDS.128) and 4 column values (one LDS.128) for 16 FFMA2:
+// Per channel a thread reads 8 row values (two broadcast LDS.128) and 8 column values (two LDS.128) for 32 FFMA2:
 // FMA-bound, where the first version (4 x 4 scalar, 8 LDS.32 per 16 FFMA) was LSU-bound.
-constexpr int kGTM = 128, kGTN = 64, kGC = 16;
+constexpr int kGTM = 128, kGTN = 128, kGC = 16;
 __global__ void __launch_bounds__(256) knn_dist_generic_kernel(const float *__restrict__ pc,
                                                                const float *__restrict__ xx, int K, int C,
                                                                float *__restrict__ dist /*[nb,K,K]*/) {
@@ -49,9 +49,9 @@ __global__ void __launch_bounds__(256) knn_dist_generic_kernel(const float *__re
   const float *p = pc + (size_t)b * K * C;
   const int i0 = blockIdx.y * kGTM, j0 = blockIdx.x * kGTN;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  float2 acc[8][2];
+  float2 acc[8][4];
 #pragma unroll
-  for (int u = 0; u < 8; ++u) acc[u][0] = acc[u][1] = make_float2(0.f, 0.f);
+  for (int u = 0; u < 8; ++u) acc[u][0] = acc[u][1] = acc[u][2] = acc[u][3] = make_float2(0.f, 0.f);
   const bool vec_ok = (C & 3) == 0 && (reinterpret_cast<uintptr_t>(pc) & 15) == 0;
   for (int c0 = 0; c0 < C; c0 += kGC) {
     __syncthreads();
@@ -86,39 +86,54 @@ __global__ void __launch_bounds__(256) knn_dist_generic_kernel(const float *__re
     for (int cc = 0; cc < cl; ++cc) {
       const float4 a0 = *reinterpret_cast<const float4 *>(&As[cc][ty * 8]);
       const float4 a1 = *reinterpret_cast<const float4 *>(&As[cc][ty * 8 + 4]);
-      const float4 bb = *reinterpret_cast<const float4 *>(&Bs[cc][tx * 4]);
+      const float4 bb = *reinterpret_cast<const float4 *>(&Bs[cc][tx * 4]);       // columns tx*4 .. +3
+      const float4 bc = *reinterpret_cast<const float4 *>(&Bs[cc][64 + tx * 4]);  // columns 64 + tx*4 .. +3 (no bank conflicts)
       const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-      const float2 b01 = make_float2(bb.x, bb.y), b23 = make_float2(bb.z, bb.w);
+      const float2 b01 = make_float2(bb.x, bb.y), b23 = make_float2(bb.z, bb.w), b45 = make_float2(bc.x, bc.y),
+                   b67 = make_float2(bc.z, bc.w);
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         acc[u][0] = __ffma2_rn(make_float2(a[u], a[u]), b01, acc[u][0]);
         acc[u][1] = __ffma2_rn(make_float2(a[u], a[u]), b23, acc[u][1]);
+        acc[u][2] = __ffma2_rn(make_float2(a[u], a[u]), b45, acc[u][2]);
+        acc[u][3] = __ffma2_rn(make_float2(a[u], a[u]), b67, acc[u][3]);
       }
     }
   }
   const float *xb = xx + (size_t)b * K;
-  const int j = j0 + tx * 4;
-  float xj[4];
+  const int j = j0 + tx * 4;  // this thread's columns: j .. j+3 and j+64 .. j+67
+  float xj[8];
 #pragma unroll
-  for (int v = 0; v < 4; ++v) xj[v] = (j + v < K) ? xb[j + v] : 0.f;
-  const bool vst = (K & 3) == 0 && (reinterpret_cast<uintptr_t>(dist) & 15) == 0 && j + 3 < K;
+  for (int v = 0; v < 8; ++v) {
+    const int jj = j + (v & 3) + ((v >> 2) << 6);
+    xj[v] = (jj < K) ? xb[jj] : 0.f;
+  }
+  const bool vst = (K & 3) == 0 && (reinterpret_cast<uintptr_t>(dist) & 15) == 0;
 #pragma unroll
   for (int u = 0; u < 8; ++u) {
     const int i = i0 + ty * 8 + u;
     if (i >= K) continue;
     const float xi = xb[i];
-    float o[4];
-    o[0] = __fadd_rn(__fadd_rn(xj[0], __fmul_rn(-2.0f, acc[u][0].x)), xi);
-    o[1] = __fadd_rn(__fadd_rn(xj[1], __fmul_rn(-2.0f, acc[u][0].y)), xi);
-    o[2] = __fadd_rn(__fadd_rn(xj[2], __fmul_rn(-2.0f, acc[u][1].x)), xi);
-    o[3] = __fadd_rn(__fadd_rn(xj[3], __fmul_rn(-2.0f, acc[u][1].y)), xi);
+    float o[8];
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      o[2 * v] = __fadd_rn(__fadd_rn(xj[2 * v], __fmul_rn(-2.0f, acc[u][v].x)), xi);
+      o[2 * v + 1] = __fadd_rn(__fadd_rn(xj[2 * v + 1], __fmul_rn(-2.0f, acc[u][v].y)), xi);
+    }
     float *dp = dist + ((size_t)b * K + i) * K + j;
-    if (vst) {
+    if (vst && j + 3 < K) {
       *reinterpret_cast<float4 *>(dp) = make_float4(o[0], o[1], o[2], o[3]);
     } else {
 #pragma unroll
       for (int v = 0; v < 4; ++v)
         if (j + v < K) dp[v] = o[v];
+    }
+    if (vst && j + 67 < K) {
+      *reinterpret_cast<float4 *>(dp + 64) = make_float4(o[4], o[5], o[6], o[7]);
+    } else {
+#pragma unroll
+      for (int v = 0; v < 4; ++v)
+        if (j + 64 + v < K) dp[64 + v] = o[4 + v];
     }
   }
 }
