@@ -29,9 +29,25 @@ def install(pointnet2=True, pytorch3d=True):
     from . import pytorch3d_ops as p3
 
     if pointnet2 and "pointnet2_ops._ext" not in sys.modules:
-        pkg = sys.modules.get("pointnet2_ops") or _module("pointnet2_ops", __path__=[])
-        pkg._ext = p2._ext
-        sys.modules["pointnet2_ops._ext"] = p2._ext
+        import importlib.util
+
+        sys.modules["pointnet2_ops._ext"] = p2._ext  # what pointnet2_utils.py:8 imports, whoever the parent package is
+        pkg = sys.modules.get("pointnet2_ops")
+        if pkg is None:
+            try:
+                real = importlib.util.find_spec("pointnet2_ops")
+            except (ImportError, ValueError):
+                real = None
+            if real is None:
+                # no reference package on sys.path: stand-alone package with hitgeom's wrappers under the same names
+                pkg = _module("pointnet2_ops", __path__=[], pointnet2_utils=p2.pointnet2_utils,
+                              pointnet2_modules=p2.pointnet2_modules)
+                sys.modules["pointnet2_ops.pointnet2_utils"] = p2.pointnet2_utils
+                sys.modules["pointnet2_ops.pointnet2_modules"] = p2.pointnet2_modules
+            # else: the reference's own pointnet2_ops package (pointnet2_ops_lib on sys.path) imports normally and its
+            # `import pointnet2_ops._ext` resolves to the entry registered above instead of JIT-compiling
+        if pkg is not None:
+            pkg._ext = p2._ext
     if pytorch3d and "pytorch3d.ops" not in sys.modules:
         pkg = sys.modules.get("pytorch3d") or _module("pytorch3d", __path__=[])
         pkg.ops = _module("pytorch3d.ops", knn_points=p3.knn_points, knn_gather=p3.knn_gather)
