@@ -74,6 +74,19 @@ SCRIPT = textwrap.dedent('''
     for cls in ("PointnetSAModuleMSG", "PointnetSAModule", "PointnetFPModule"):
         same_signature(getattr(ref_pm, cls).__init__, getattr(pm, cls).__init__)
         same_signature(getattr(ref_pm, cls).forward, getattr(pm, cls).forward)
+    # the callers: they import, find pytorch3d.ops / pointnet2_ops through hitgeom, and hitgeom's rebuilt versions keep
+    # their constructor / call contracts
+    sys.modules["matplotlib.pyplot"].figure = lambda *a, **k: None
+    from ShapeAttack.HiT_ADV import HiT_ADV as RefHiT
+    from hitgeom.hit_adv import HiT_ADV
+    same_signature(RefHiT.__init__, HiT_ADV.__init__)
+    same_signature(RefHiT.attack, HiT_ADV.attack)
+    import FGM.GeoA3_args as ref_geo                                        # -> pointnet2_ops_lib.pointnet2_ops.pointnet2_utils
+    assert ref_geo.pointnet2_utils._ext is sys.modules["pointnet2_ops._ext"]
+    assert ref_geo.knn_points is sys.modules["pytorch3d.ops"].knn_points
+    pa = list(inspect.signature(ref_geo.uniform_loss).parameters)
+    assert list(inspect.signature(em.uniform_loss).parameters) == pa, pa
+    same_signature(ref_geo.kNN_smoothing_loss, em.kNN_smoothing_loss)
     print("DROPIN_OK")
 ''')
 
