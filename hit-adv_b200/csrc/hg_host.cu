@@ -31,6 +31,19 @@ struct hgHostStep {
 
 namespace {
 
+// the session's buffers and streams live on the device that was current at creation: calls run there whatever the
+// caller's current device is, and put it back afterwards
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev); else prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
 // per cloud: total = w (cw * pick(loss1, loss2) + kw * lossk); upstream scales of the three partial losses
 __global__ void host_step_scales_kernel(const float *__restrict__ loss1, const float *__restrict__ loss2,
                                         const float *__restrict__ lossk, const float *__restrict__ w, int n, int method,
@@ -127,7 +140,9 @@ HG_API hgHostStep *hg_host_step_create(int N, int chunk_clouds, int knn_k_max) {
 }
 
 HG_API void hg_host_step_destroy(hgHostStep *s) {
-  if (s) free_session(s);
+  if (!s) return;
+  DeviceGuard guard(s->device);
+  free_session(s);
 }
 
 HG_API int hg_chamfer_knn_step_host_f32(hgHostStep *s, const float *adv_h, const float *ori_h, int B,
@@ -141,6 +156,7 @@ HG_API int hg_chamfer_knn_step_host_f32(hgHostStep *s, const float *adv_h, const
              knn_k, s->k1max - 1);
   const int N = s->N, k1 = knn_k + 1;
   const float inv_b = 1.0f / (float)B;
+  DeviceGuard guard(s->device);
   if (B > s->loss_cap) {
     if (s->loss_pinned) cudaFreeHost(s->loss_pinned);
     s->loss_pinned = nullptr;

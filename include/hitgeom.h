@@ -210,7 +210,8 @@ int hg_edge_feature_grad_f32(const float *grad_out, const int64_t *idx, int B, i
  *   grad_adv = d loss / d adv.   chamfer_method: 0 'adv2ori', 1 'ori2adv', 2 'both' (dist_utils.py:44-80).
  * The batch is pipelined in chunks of `chunk_clouds` over two streams with their own device buffers (owned by the
  * session), so host<->device copies hide behind the kernels; the call returns when loss and gradient are in place.
- * A session serves any B and any knn_k <= knn_k_max for its N; it is bound to the device current at creation.
+ * A session serves any B and any knn_k <= knn_k_max for its N; it lives on the device current at creation (calls
+ * switch to that device and restore the caller's) and is not thread-safe.
  * ------------------------------------------------------------------------------------------------------- */
 typedef struct hgHostStep hgHostStep;
 hgHostStep *hg_host_step_create(int N, int chunk_clouds, int knn_k_max); /* NULL on failure (hg_last_error) */
