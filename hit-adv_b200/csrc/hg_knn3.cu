@@ -1,7 +1,8 @@
 // hg_knn3.cu -- streaming k-nearest-neighbour selection for 3-D points (KNNDist, DGCNN layer 1, knn_points).
 //
-// Per (query, candidate) pair the FMA pipe does the same 5 operations as the Chamfer kernel (FMUL, 2 FFMA,
-// 2 FADD, issued packed as FMUL2/FFMA2/FADD2 over two CANDIDATES at a time); what differs is the selection.
+// Per (query, candidate) pair the reference's distance is the same 5 FMA-pipe operations as in the Chamfer kernel
+// (FMUL, 2 FFMA, 2 FADD, issued packed as FMUL2/FFMA2/FADD2 over two CANDIDATES at a time; the self-kNN path filters
+// with a 4-operation folded form, see filter_addend); what differs is the selection.
 // A sorted-insertion test per pair would make every warp take the slow path on almost every candidate
 // (32 lanes x QT queries, each inserting ~k ln(N/k) times), and even a compare per pair costs issue slots the
 // FMA pipe cannot hide on this part (FMNMX + FSETP + SEL ~ 5 slots next to 10.5 for the arithmetic, see
@@ -329,7 +330,8 @@ int launch_form(const float *q, const float *r, int B, int Nq, int Nr, int k1, f
 
 // ---- threshold seeding for self-kNN ---------------------------------------------------------------------------
 // A uniform grid over the cloud's bounding box (about 3 points per cell) gives every query an exact UPPER BOUND on its
-// KM-th smallest distance: the KM-th smallest over the points of its 27 neighbouring cells, evaluated with the same
+// KM-th smallest distance: the KM-th smallest over the points of its neighbouring cells (the 2x2x2 nearest ones for
+// lists up to 20 entries, all 27 beyond), evaluated with the same
 // expanded-form arithmetic (those points are real candidates, so the true KM-th distance cannot be larger).  The
 // brute-force pass still evaluates all N^2 pairs and still decides every index itself; the seed only spares the
 // ~KM ln(N/KM) insertions a cold threshold costs.  The bound is nudged up one ulp so that the strict '<' of the
