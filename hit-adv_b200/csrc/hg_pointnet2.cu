@@ -34,9 +34,9 @@ int ref_opt_n_threads(int work_size) {
 
 // ---- gather / group (sampling_gpu.cu:8-20, group_points_gpu.cu:8-28) ---------------------------------------
 // out[b,c,e] = points[b,c,idx[b,e]],  e over the flattened index tensor (m, or npoints*nsample).
-// HBM-bound on the output write: one CTA row per (b,c) plane, four consecutive e per thread (int4 index load,
-// four gathers that hit L1/L2 -- a plane of n floats is a few KB --, one float4 store), no integer division.
-// SMEM: the (b,c) source plane (n floats) is staged in shared memory first -- random 4-byte gathers from L1 cost one
+// HBM-bound on the output write: four consecutive e per thread (one int4 index load, four gathers per channel, one
+// streaming float4 store per channel), no integer division.
+// SMEM: the source planes (n floats each) are staged in shared memory first -- random 4-byte gathers from L1 cost one
 // wavefront per distinct line and cap the kernel near 2 TB/s; from shared memory they cost a few bank cycles.
 // A CTA pass covers kGatherCP channels of one cloud, so that every index load serves kGatherCP output rows.
 constexpr int kGatherCP = 4;
