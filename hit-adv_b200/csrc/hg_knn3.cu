@@ -283,6 +283,10 @@ __global__ void __launch_bounds__(kThreads) knn3_kernel(const float *__restrict_
   }
 }
 
+// Test-only override of the instantiation launch_form / launch_qt would pick from the problem size (0 = automatic):
+// lets small seeded inputs reach every (QT, GP) variant, including the ones only large batches select.
+static int g_force_qt = 0, g_force_gp = 0;
+
 template <int FORM, int QT, int KM, typename IdxT>
 int launch_qt(const float *q, const float *r, int B, int Nq, int Nr, int k1, float *vals, IdxT *idx,
               const float *thr0, const float *sbound, cudaStream_t stream) {
@@ -290,7 +294,7 @@ int launch_qt(const float *q, const float *r, int B, int Nq, int Nr, int k1, flo
   const bool prof = hg_prof_begin(HG_PROF_KNN, stream);
   // 8 candidates per hit bit (512-candidate tiles) for long candidate lists, 4 (256) for short ones, where the
   // cheaper group re-evaluation in the drain outweighs the extra mask updates (measured cross-over ~2-4k)
-  if (Nr < 2048)
+  if (g_force_gp ? g_force_gp == 2 : Nr < 2048)
     knn3_kernel<FORM, QT, KM, 2, IdxT><<<grid, kThreads, 0, stream>>>(q, r, Nq, Nr, k1, vals, idx, thr0, sbound);
   else
     knn3_kernel<FORM, QT, KM, 4, IdxT><<<grid, kThreads, 0, stream>>>(q, r, Nq, Nr, k1, vals, idx, thr0, sbound);
@@ -313,6 +317,19 @@ int launch_form(const float *q, const float *r, int B, int Nq, int Nr, int k1, f
   const long long want = 2LL * hg_sm_count();
   auto ctas = [&](int qt) { return (long long)B * ((Nq + qt * kThreads - 1) / (qt * kThreads)); };
   const bool short_list = Nr < 2048;
+  if (g_force_qt) {
+    const int qt = g_force_qt;
+    if (k1 <= 6 && qt == 4) return launch_qt<FORM, 4, 6, IdxT>(q, r, B, Nq, Nr, k1, vals, idx, thr0, sbound, stream);
+    if (k1 <= 6 && qt == 2) return launch_qt<FORM, 2, 6, IdxT>(q, r, B, Nq, Nr, k1, vals, idx, thr0, sbound, stream);
+    if (k1 <= 6 && qt == 1) return launch_qt<FORM, 1, 6, IdxT>(q, r, B, Nq, Nr, k1, vals, idx, thr0, sbound, stream);
+    if (k1 > 6 && k1 <= 20 && qt == 2)
+      return launch_qt<FORM, 2, 20, IdxT>(q, r, B, Nq, Nr, k1, vals, idx, thr0, sbound, stream);
+    if (k1 > 6 && k1 <= 20 && qt == 1)
+      return launch_qt<FORM, 1, 20, IdxT>(q, r, B, Nq, Nr, k1, vals, idx, thr0, sbound, stream);
+    if (k1 > 20 && qt == 1) return launch_qt<FORM, 1, 32, IdxT>(q, r, B, Nq, Nr, k1, vals, idx, thr0, sbound, stream);
+    hg_set_error("knn: forced QT=%d has no instantiation for k=%d", qt, k1);
+    return HG_E_UNSUPPORTED;
+  }
   if (k1 <= 6) {
     if (!short_list && Nq >= 3 * kThreads && ctas(4) >= want)
       return launch_qt<FORM, 4, 6, IdxT>(q, r, B, Nq, Nr, k1, vals, idx, thr0, sbound, stream);
@@ -544,6 +561,11 @@ static int g_seed_min_n = 0, g_seed_near8 = 0;
 HG_API void hg_knn_tune(int seed_min_n, int near8) {
   g_seed_min_n = seed_min_n;
   g_seed_near8 = near8;
+}
+
+HG_API void hg_knn_force_shape(int qt, int gp) {
+  g_force_qt = qt;
+  g_force_gp = gp;
 }
 
 // self-kNN (expanded form) with grid-seeded thresholds; falls back to the unseeded launch for small clouds

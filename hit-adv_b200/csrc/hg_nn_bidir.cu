@@ -443,6 +443,10 @@ int launch_main(const NnParams &p, int B, cudaStream_t stream) {
   dim3 grid((p.N2 + p.RB - 1) / p.RB, (ncg + WARPS - 1) / WARPS, B);
   const size_t smem = (size_t)(p.RB + 4) * sizeof(float4) + (size_t)WARPS * (p.RB / 2) * sizeof(uint4) +
                       (size_t)2 * T * WARPS * 32 * sizeof(float);
+  if (smem > 48 * 1024) {  // only reachable through hg_nn_bidir_tune (automatic RB <= 512 stays under 48 KB)
+    HG_REQUIRE(smem <= 200 * 1024, HG_E_UNSUPPORTED, "nn_bidir: RB=%d needs %zu bytes of shared memory", p.RB, smem);
+    HG_CUDA(cudaFuncSetAttribute(nn_bidir_d3_kernel<T, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
   const bool prof = hg_prof_begin(HG_PROF_NN_BIDIR, stream);
   nn_bidir_d3_kernel<T, WARPS><<<grid, WARPS * 32, smem, stream>>>(p);
   hg_prof_end(HG_PROF_NN_BIDIR, stream, prof);

@@ -25,6 +25,7 @@ _SIGNATURES = {
     "hg_nn_bidir_f32": (I, [P, P, I, I, I, I, P, P, P, P, P, Z, P]),
     "hg_nn_bidir_tune": (None, [I, I]),
     "hg_knn_tune": (None, [I, I]),
+    "hg_knn_force_shape": (None, [I, I]),
     "hg_launch_count": (ctypes.c_ulonglong, []),
     "hg_prof_enable": (None, [I]),
     "hg_prof_read": (I, [I, ctypes.POINTER(F), ctypes.POINTER(I)]),

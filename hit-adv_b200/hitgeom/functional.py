@@ -350,5 +350,10 @@ def tune_nn_bidir(T=0, RB=0):
     lib().hg_nn_bidir_tune(int(T), int(RB))
 
 
+def force_knn_shape(qt=0, gp=0):
+    """Test-only override of the streaming kNN kernel's instantiation (queries per lane, pairs per filter bit)."""
+    lib().hg_knn_force_shape(int(qt), int(gp))
+
+
 __all__ = [n for n in dir() if not n.startswith("_")]
 _ = _lib

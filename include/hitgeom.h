@@ -57,6 +57,10 @@ void hg_nn_bidir_tune(int T, int RB);
 /* Benchmark-only overrides: smallest cloud size whose self-kNN gets grid-seeded thresholds (0 = default), and the
  * seed scan's cell neighbourhood (0 = automatic, 1 = 2x2x2, 2 = 3x3x3). */
 void hg_knn_tune(int seed_min_n, int neighbourhood);
+/* Test-only override of the streaming 3-D kNN kernel's instantiation: qt = queries per lane (1, 2, 4), gp = candidate
+ * pairs per filter bit (2, 4); 0 = chosen from the problem size.  A combination that is not instantiated for the
+ * requested k makes the next kNN call fail with HG_E_UNSUPPORTED.  Process-global, not thread-safe. */
+void hg_knn_force_shape(int qt, int gp);
 
 /* ---------------------------------------------------------------------------------------------------------
  * util/set_distance.py:15-32,45-48,65-68 -- `_Distance.batch_pairwise_dist` fused with the two `torch.min`

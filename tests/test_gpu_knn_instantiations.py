@@ -1,0 +1,114 @@
+"""Every instantiation of the streaming 3-D kNN kernel against the oracle, bit for bit.
+
+`launch_form` (hit-adv_b200/csrc/hg_knn3.cu) picks queries-per-lane (QT), list length (KM) and candidate pairs per
+filter bit (GP) from the batch size, the cloud size and the SM count, so small seeded inputs only ever reach QT = 1.
+The headline benchmark (config 5 shard, 1024 x 16384) runs `knn3_kernel<FOLD4, QT=4, KM=6, GP=4>`; config 1
+(388 x 1024) runs the small-cloud kernel.  Here `hg_knn_force_shape` makes small inputs reach EVERY (QT, GP) pair, and
+three batches large enough to select the big-batch variants naturally are checked as well.  Values and indices
+(canonical lowest-index-first tie order) must equal `oracle.knn_self` / `oracle.knn_points` exactly; the inputs
+include exact duplicates (ties), near-origin points and a cloud far from the origin (where the folded filter's slack
+matters).  Reference: util/dist_utils.py:148-156, model/dgcnn_cls.py:7-13."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from util_inputs import clouds, jitter
+
+pytestmark = pytest.mark.gpu
+
+
+def gpu(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+@pytest.fixture()
+def F():
+    from hitgeom import functional
+
+    yield functional
+    functional.force_knn_shape(0, 0)
+
+
+def _inputs(n):
+    a = clouds(3, n, 1000 + n, "surface")
+    a[1, : n // 4] = a[1, n // 4 : 2 * (n // 4)]  # a quarter of cloud 1 duplicated: exact ties
+    b = (clouds(2, n, 77 + n, "gauss") * 0.05 + np.asarray((60.0, -35.0, 20.0), np.float32)).astype(np.float32)
+    b[0, :32] = b[0, 32:64]
+    return [("surface+dups", a), ("far from origin", b)]
+
+
+QT_FOR_K = {6: (1, 2, 4), 5: (1, 2, 4), 1: (4,), 20: (1, 2), 12: (2,), 32: (1,), 21: (1,)}
+
+
+@pytest.mark.parametrize("n", [2048, 1024, 3000, 333])
+@pytest.mark.parametrize("gp", [2, 4])
+@pytest.mark.parametrize("k1", sorted(QT_FOR_K))
+def test_self_knn_every_forced_instantiation(oracle, F, n, gp, k1):
+    """Self-kNN (KNNDist, DGCNN layer 1): n >= 2048 takes the grid-seeded folded-filter path, n < 2048 the small-cloud
+    path; every QT the list length admits, both GP."""
+    for tag, pc in _inputs(n):
+        ov, oi = oracle.knn_self(pc, k1, threads=oracle.host_threads())
+        for qt in QT_FOR_K[k1]:
+            F.force_knn_shape(qt, gp)
+            vals, idx = F.knn_self(gpu(pc), k1)
+            assert np.array_equal(vals.cpu().numpy(), ov), (tag, n, qt, gp, k1, "values")
+            assert np.array_equal(idx.cpu().numpy(), oi), (tag, n, qt, gp, k1, "indices")
+
+
+def test_forced_shape_without_instantiation_fails_loudly(F):
+    from hitgeom._lib import HitgeomError
+
+    F.force_knn_shape(4, 4)
+    with pytest.raises(HitgeomError):
+        F.knn_self(gpu(clouds(1, 2048, 3)), 20)  # QT = 4 exists for lists of <= 6 entries only
+
+
+@pytest.mark.parametrize("gp", [2, 4])
+@pytest.mark.parametrize("k1,qts", [(6, (1, 2, 4)), (17, (1, 2)), (32, (1,))])
+def test_knn_points_every_forced_instantiation(oracle, F, gp, k1, qts):
+    """DIRECT form (pytorch3d.ops.knn_points stand-in; parity unpinned upstream, pinned to the oracle's restatement)."""
+    from hitgeom.functional import knn_points_raw
+
+    p1 = clouds(2, 700, 5, "surface")
+    p2 = clouds(2, 2300, 6, "surface")
+    p2[1, :100] = p2[1, 100:200]
+    od, oi = oracle.knn_points(p1, p2, k1)
+    for qt in qts:
+        F.force_knn_shape(qt, gp)
+        d, i = knn_points_raw(gpu(p1), gpu(p2), k1)
+        assert np.array_equal(d.cpu().numpy(), od) and np.array_equal(i.cpu().numpy(), oi), (qt, gp, k1)
+
+
+@pytest.mark.parametrize("gp", [2, 4])
+@pytest.mark.parametrize("k1,qts", [(6, (1, 2, 4)), (20, (1, 2))])
+def test_unseeded_expanded_form_every_forced_instantiation(oracle, F, gp, k1, qts):
+    """The 5-operation EXPANDED filter (what hg_knn_self_f32 runs when the caller passes no workspace)."""
+    from hitgeom._lib import check, lib, ptr, stream_ptr
+
+    pc = _inputs(1500)[0][1]
+    ov, oi = oracle.knn_self(pc, k1, threads=4)
+    B, K, _ = pc.shape
+    x = gpu(pc)
+    for qt in qts:
+        F.force_knn_shape(qt, gp)
+        vals = torch.empty((B, K, k1), dtype=torch.float32, device="cuda")
+        idx = torch.empty((B, K, k1), dtype=torch.int32, device="cuda")
+        check(lib().hg_knn_self_f32(ptr(x), B, K, 3, k1, ptr(vals), ptr(idx), None, ctypes.c_size_t(0), stream_ptr()),
+              "hg_knn_self_f32")
+        assert np.array_equal(vals.cpu().numpy(), ov) and np.array_equal(idx.cpu().numpy(), oi), (qt, gp, k1)
+
+
+@pytest.mark.parametrize("B,n,k1", [(80, 2048, 6), (160, 2048, 20), (12, 16384, 6), (388, 1024, 6), (300, 1024, 20)])
+def test_big_batch_variants_selected_naturally(oracle, F, B, n, k1):
+    """Batches large enough for launch_form to pick the big-batch instantiations by itself (no override): on a
+    148-SM part 80 x 2048 / k+1 = 6 and 12 x 16384 select <FOLD4, QT=4, KM=6, GP=4> -- the headline kernel of
+    bench.py's config-5 shard -- 160 x 2048 / k+1 = 20 selects <FOLD4, 2, 20, 4>, 388 x 1024 is config 1."""
+    F.force_knn_shape(0, 0)
+    pc = jitter(clouds(B, n, 4242 + n, "surface" if B < 100 else "gauss"), 3)
+    pc[0, : n // 8] = pc[0, n // 8 : 2 * (n // 8)]
+    vals, idx = F.knn_self(gpu(pc), k1)
+    ov, oi = oracle.knn_self(pc, k1, threads=oracle.host_threads())
+    assert np.array_equal(vals.cpu().numpy(), ov)
+    assert np.array_equal(idx.cpu().numpy(), oi)
