@@ -55,7 +55,7 @@ class HiT_ADV:
         self.alpha = alpha
         self.total_central_num = total_central_num
         self.iterations_run = 0  # inner iterations of the last attack() call (for the benchmark)
-        self.loop_ms = 0.0
+        self._loop_events = None
 
     # ---- helpers (HiT_ADV.py:298-346) ---------------------------------------------------------------------------
     @staticmethod
@@ -146,7 +146,14 @@ class HiT_ADV:
 
     # ---- the attack ---------------------------------------------------------------------------------------------
     def attack(self, data, target):
-        """data [B,K,6] (xyz + normal), target [B] -> (best adversarial clouds [B,K,3] float64 numpy, success count)."""
+        """data [B,K,6] (xyz + normal), target [B] -> (best adversarial clouds [B,K,3] float64 numpy, success count)
+        -- the reference's return contract (HiT_ADV.py:114,284-287)."""
+        adv, success_num = self.attack_device(data, target)
+        return adv.double().cpu().numpy(), success_num.cpu()
+
+    def attack_device(self, data, target):
+        """Same attack; the results stay on the device: (adversarial clouds [B,K,3] float32 CUDA tensor, success count
+        0-d CUDA tensor).  What `sharding.run_sharded` all-gathers over NCCL without a host round trip."""
         B, K = data.shape[:2]
         dev = torch.device("cuda", torch.cuda.current_device())
         ori_data = data[:, :, :3].float().to(dev).clone().detach().transpose(1, 2).contiguous()  # [B,3,K]
@@ -215,6 +222,13 @@ class HiT_ADV:
             failed = lower_bound == 0.
             o_bestattack = torch.where(failed[:, None, None], tmp_adv_data.detach(), o_bestattack)
             success_num = (lower_bound > 0.).sum()
-        out = o_bestattack.transpose(1, 2).double().cpu().numpy(), success_num.cpu()
-        self.loop_ms = ev0.elapsed_time(ev1)  # device time of the iteration loops of this call (benchmark)
-        return out
+        out = o_bestattack.transpose(1, 2).contiguous()
+        self._loop_events = (ev0, ev1)
+        return out, success_num
+
+    @property
+    def loop_ms(self):
+        """Device time [ms] of the iteration loops of the last attack() call (synchronises on its end event)."""
+        ev0, ev1 = self._loop_events
+        ev1.synchronize()
+        return ev0.elapsed_time(ev1)

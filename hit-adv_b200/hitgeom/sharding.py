@@ -57,21 +57,39 @@ def shard(t, r=None, w=None):
     return t[lo:hi]
 
 
-def gather_clouds(local, n_total):
-    """all_gather of per-rank result blocks [n_r, ...] -> [n_total, ...] on every rank (ragged tail padded)."""
+def gather_clouds(local, n_total, timing=None):
+    """all_gather of per-rank result blocks [n_r, ...] -> [n_total, ...] on every rank (ragged tail padded).
+
+    `timing` (optional dict) receives the collective's record: op, payload bytes, and -- for CUDA tensors -- a pair of
+    CUDA events bracketing it on the current stream (`timing["events"]`; read them after a synchronize)."""
     w = world()
+    if timing is not None:
+        timing.update(op="all_gather_into_tensor", world=w, bytes_per_rank=int(local.numel() * local.element_size()),
+                      bytes_total=int(local.numel() * local.element_size()) * w, events=None)
     if w == 1:
         return local
+    ev = None
+    if timing is not None and local.is_cuda:
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record()
     per = (n_total + w - 1) // w
-    pad = torch.zeros((per,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
-    pad[: local.shape[0]] = local
-    out = torch.empty((w * per,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
-    dist.all_gather_into_tensor(out, pad)
-    pieces = []
-    for r in range(w):
-        lo, hi = shard_range(n_total, r, w)
-        pieces.append(out[r * per : r * per + (hi - lo)])
-    return torch.cat(pieces, dim=0)
+    if n_total % w == 0 and local.shape[0] == per and local.is_contiguous():  # equal blocks: no padding, no re-cut
+        out = torch.empty((n_total,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(out, local)
+    else:
+        pad = torch.zeros((per,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        pad[: local.shape[0]] = local
+        full = torch.empty((w * per,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(full, pad)
+        pieces = []
+        for r in range(w):
+            lo, hi = shard_range(n_total, r, w)
+            pieces.append(full[r * per : r * per + (hi - lo)])
+        out = torch.cat(pieces, dim=0)
+    if ev is not None:
+        ev[1].record()
+        timing["events"] = ev
+    return out
 
 
 def reduce_counters(counters, device=None):
@@ -102,10 +120,11 @@ def barrier():
         dist.barrier()
 
 
-def run_sharded(fn, data, *extra):
+def run_sharded(fn, data, *extra, timing=None):
     """Run `fn(local_data, *local_extra) -> (local_result [n_r,...], counters dict)` on this rank's block of
-    instances and return (all results [n,...], summed counters) on every rank."""
+    instances and return (all results [n,...], summed counters) on every rank.  `timing`: see gather_clouds."""
     n = data.shape[0]
     lo, hi = shard_range(n)
     result, counters = fn(data[lo:hi], *[e[lo:hi] for e in extra])
-    return gather_clouds(result, n), reduce_counters(counters, device=result.device if result.is_cuda else None)
+    return (gather_clouds(result, n, timing=timing),
+            reduce_counters(counters, device=result.device if result.is_cuda else None))
