@@ -133,4 +133,4 @@ int hg_knn3_launch_i64(int form, const float *q, const float *r, int B, int Nq, 
                        long long *idx, cudaStream_t stream);
 size_t hg_knn3_seed_workspace_bytes(int B, int N);
 int hg_knn3_self_seeded_i32(const float *pc, int B, int N, int k1, float *vals, int *idx, void *workspace,
-                            size_t workspace_bytes, cudaStream_t stream);
+                            size_t workspace_bytes, cudaStream_t stream, int *idx_state = nullptr, int state_valid = 0);

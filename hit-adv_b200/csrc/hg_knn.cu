@@ -382,12 +382,18 @@ HG_API size_t hg_knn_self_workspace_bytes(int B, int K, int C, int k1) {
 
 HG_API int hg_knn_self_f32(const float *pc, int B, int K, int C, int k1, float *vals, int *idx, void *workspace,
                            size_t workspace_bytes, hgStream stream_) {
+  return hg_knn_self_temporal_f32(pc, B, K, C, k1, vals, idx, nullptr, 0, workspace, workspace_bytes, stream_);
+}
+
+HG_API int hg_knn_self_temporal_f32(const float *pc, int B, int K, int C, int k1, float *vals, int *idx, int *idx_state,
+                                    int state_valid, void *workspace, size_t workspace_bytes, hgStream stream_) {
   cudaStream_t stream = hg_stream(stream_);
   HG_REQUIRE(pc && idx, HG_E_BADARG, "knn_self: null pointer");
   HG_REQUIRE(B > 0 && K > 0 && C > 0, HG_E_BADARG, "knn_self: sizes must be positive");
   HG_REQUIRE(k1 >= 1 && k1 <= 32 && k1 <= K, HG_E_BADARG, "knn_self: need 1 <= k <= min(32, K); got k=%d K=%d", k1, K);
   HG_REQUIRE(B <= 65535, HG_E_UNSUPPORTED, "knn_self: B=%d > 65535 clouds per call", B);
-  if (C == 3) return hg_knn3_self_seeded_i32(pc, B, K, k1, vals, idx, workspace, workspace_bytes, stream);
+  if (C == 3)
+    return hg_knn3_self_seeded_i32(pc, B, K, k1, vals, idx, workspace, workspace_bytes, stream, idx_state, state_valid);
   const size_t need = hg_knn_self_workspace_bytes(B, K, C, k1);
   HG_REQUIRE(workspace && workspace_bytes >= need, HG_E_WORKSPACE, "knn_self: workspace too small (%zu < %zu)",
              workspace_bytes, need);

@@ -130,7 +130,8 @@ __global__ void __launch_bounds__(kThreads) knn3_kernel(const float *__restrict_
                                                         float *__restrict__ vals, IdxT *__restrict__ idx,
                                                         const float *__restrict__ thr0 /*[B,Nq] or null*/,
                                                         const float *__restrict__ sbound /*FOLD4: [B] stride 8,
-                                                        upper bound on max |candidate|^2*/) {
+                                                        upper bound on max |candidate|^2*/,
+                                                        int *__restrict__ idx_state /*second copy of idx or null*/) {
   constexpr int kTilePairs = 32 * GP;
   constexpr int kTileC = 2 * kTilePairs;
   __shared__ float4 cand[2 * kTilePairs];  // two float4 per candidate pair
@@ -277,9 +278,314 @@ __global__ void __launch_bounds__(kThreads) knn3_kernel(const float *__restrict_
         if (s < k1) {
           if (vals) vals[((size_t)b * Nq + i) * k1 + s] = top[t].v[s];
           idx[((size_t)b * Nq + i) * k1 + s] = (IdxT)top[t].id[s];
+          if (idx_state) idx_state[((size_t)b * Nq + i) * k1 + s] = top[t].id[s];
         }
       }
     }
+  }
+}
+
+// ---- small clouds (< 2k points): whole candidate set resident in shared memory, drain deferred -----------------
+// At 1024 points the streaming kernel above spends more time in its per-tile drains than in its main loop: with 8
+// tiles, every tile ends in a divergent drain that lasts as long as the unluckiest lane's hits, and the cold
+// thresholds of the first tile flag most candidates.  Here
+//   * every query starts from an exact upper bound on its k-th distance (knn_seed_small_kernel: a uniform grid built
+//     in shared memory by one CTA per cloud), so the filter is tight from the first candidate;
+//   * the whole cloud is staged once (16 B per candidate), the main loop runs over ALL candidate pairs without a
+//     barrier or a drain, storing one mask word per 32 groups in shared memory;
+//   * ONE drain at the end walks the flagged groups of all words in a single loop: its length is the largest number of
+//     flagged groups any lane has in total, not the sum over tiles of the per-tile maxima.
+// A word in which some lane flags more than kDrainNow groups (a loose or infinite seed) triggers an immediate drain,
+// which tightens that lane's threshold, so correctness and progress never depend on the quality of the seeds.
+constexpr int kDrainNow = 12;
+
+template <int QT, int KM, int GP>
+__global__ void __launch_bounds__(kThreads) knn3_small_kernel(const float *__restrict__ pc, int N, int k1, int W,
+                                                              float *__restrict__ vals, int *__restrict__ idx,
+                                                              const float *__restrict__ thr0 /*[B,N]*/,
+                                                              const float *__restrict__ sbound /*[B] stride 8*/,
+                                                              int *__restrict__ idx_state /*second copy or null*/) {
+  constexpr int FORM = HG_KNN_FORM_EXPANDED_FOLD4;
+  extern __shared__ float4 smem4[];
+  const int npairs = W * 32 * GP;               // padded to whole mask words
+  float4 *cand = smem4;                         // two float4 per candidate pair
+  unsigned *smask = reinterpret_cast<unsigned *>(cand + 2 * (size_t)npairs);  // [QT][W][kThreads]
+  const int b = blockIdx.y, tid = threadIdx.x;
+  const float *p = pc + (size_t)b * N * 3;
+
+  for (int pr = tid; pr < npairs; pr += kThreads) {
+    float c[2][4];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int j = 2 * pr + h;
+      c[h][0] = c[h][1] = c[h][2] = 0.f;
+      c[h][3] = CUDART_INF_F;
+      if (j < N) {
+        const float x = __ldg(p + (size_t)j * 3), y = __ldg(p + (size_t)j * 3 + 1), z = __ldg(p + (size_t)j * 3 + 2);
+        c[h][0] = x; c[h][1] = y; c[h][2] = z;
+        c[h][3] = hg_sumsq3_seq(x, y, z);
+      }
+    }
+    cand[2 * pr] = make_float4(c[0][0], c[1][0], c[0][1], c[1][1]);
+    cand[2 * pr + 1] = make_float4(c[0][2], c[1][2], c[0][3], c[1][3]);
+  }
+
+  float a0[QT], a1[QT], a2[QT], a3[QT], af[QT], seed[QT], S[QT];
+  unsigned nz[QT];
+  TopK<KM> top[QT];
+  const float cmax = sqrtf(sbound[(size_t)b * 8]);
+#pragma unroll
+  for (int t = 0; t < QT; ++t) {
+    const int i = (blockIdx.x * QT + t) * kThreads + tid;
+    float q0 = 0.f, q1 = 0.f, q2 = 0.f;
+    if (i < N) {
+      q0 = __ldg(p + (size_t)i * 3);
+      q1 = __ldg(p + (size_t)i * 3 + 1);
+      q2 = __ldg(p + (size_t)i * 3 + 2);
+    }
+    a0[t] = -2.0f * q0;
+    a1[t] = -2.0f * q1;
+    a2[t] = -2.0f * q2;
+    a3[t] = hg_sumsq3_seq(q0, q1, q2);
+    seed[t] = (i < N) ? thr0[(size_t)b * N + i] : -CUDART_INF_F;  // lanes past the cloud never flag anything
+    S[t] = (sqrtf(a3[t]) + cmax) * (sqrtf(a3[t]) + cmax) * 1.0001f;
+    af[t] = filter_addend<FORM>(a3[t], seed[t], S[t]);
+    nz[t] = 0u;
+    top[t].init();
+  }
+  __syncthreads();
+
+  // flagged groups of the pending words of query t, ascending; thresholds refreshed after every group
+  auto drain = [&](int t) {
+    unsigned pend = nz[t], m = 0u;
+    int w = 0;
+    while (true) {
+      if (m == 0u) {
+        if (pend == 0u) break;
+        w = __ffs(pend) - 1;
+        pend &= pend - 1u;
+        m = smask[((size_t)t * W + w) * kThreads + tid];  // non-zero by construction
+      }
+      const int pos = 31 - __clz(m);
+      m &= ~(1u << pos);
+      const int grp = w * 32 + (31 - pos);
+      const float4 *cp = cand + 2 * GP * grp;
+      unsigned sub = 0u;  // after 2*GP shifts, bit 2*GP-1-c belongs to candidate c of the group
+#pragma unroll
+      for (int u = 0; u < GP; ++u) {
+        const float4 cA = cp[2 * u], cB = cp[2 * u + 1];
+        const float2 e = filter_value<FORM>(a0[t], a1[t], a2[t], af[t], cA, cB);
+        sub = __funnelshift_l(__float_as_uint(e.x), sub, 1);
+        sub = __funnelshift_l(__float_as_uint(e.y), sub, 1);
+      }
+      while (sub) {
+        const int sp = 31 - __clz(sub);
+        sub &= ~(1u << sp);
+        const int c = 2 * GP - 1 - sp;
+        const float4 cA = cp[2 * (c >> 1)], cB = cp[2 * (c >> 1) + 1];
+        const bool hi = c & 1;
+        top[t].push(knn_dist_exact<FORM>(a0[t], a1[t], a2[t], a3[t], hi ? cA.y : cA.x, hi ? cA.w : cA.z,
+                                         hi ? cB.y : cB.x, hi ? cB.w : cB.z),
+                    2 * GP * grp + c);
+      }
+      af[t] = filter_addend<FORM>(a3[t], fminf(seed[t], top[t].v[KM - 1]), S[t]);
+    }
+    nz[t] = 0u;
+  };
+
+  for (int w = 0; w < W; ++w) {
+    unsigned mk[QT];
+#pragma unroll
+    for (int t = 0; t < QT; ++t) mk[t] = 0u;
+    const float4 *wp = cand + (size_t)2 * GP * 32 * w;
+#pragma unroll (KM <= 6 ? 2 : 1)
+    for (int g = 0; g < 32; ++g) {
+      const float4 *cp = wp + 2 * GP * g;
+      float4 cA[GP], cB[GP];
+#pragma unroll
+      for (int u = 0; u < GP; ++u) {
+        cA[u] = cp[2 * u];
+        cB[u] = cp[2 * u + 1];
+      }
+#pragma unroll
+      for (int t = 0; t < QT; ++t) {
+        unsigned o = 0u;
+#pragma unroll
+        for (int u = 0; u < GP; ++u) {
+          const float2 e = filter_value<FORM>(a0[t], a1[t], a2[t], af[t], cA[u], cB[u]);
+          o |= __float_as_uint(e.x) | __float_as_uint(e.y);
+        }
+        mk[t] = __funnelshift_l(o, mk[t], 1);  // after 32 shifts, bit 31-g belongs to group g of this word
+      }
+    }
+    bool crowded = false;
+#pragma unroll
+    for (int t = 0; t < QT; ++t) {
+      smask[((size_t)t * W + w) * kThreads + tid] = mk[t];
+      if (mk[t]) nz[t] |= 1u << w;
+      crowded |= __popc(mk[t]) > kDrainNow;
+    }
+    if (__any_sync(0xffffffffu, crowded)) {
+#pragma unroll
+      for (int t = 0; t < QT; ++t) drain(t);
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < QT; ++t) drain(t);
+
+#pragma unroll
+  for (int t = 0; t < QT; ++t) {
+    const int i = (blockIdx.x * QT + t) * kThreads + tid;
+    if (i < N) {
+#pragma unroll
+      for (int s = 0; s < KM; ++s) {
+        if (s < k1) {
+          if (vals) vals[((size_t)b * N + i) * k1 + s] = top[t].v[s];
+          idx[((size_t)b * N + i) * k1 + s] = top[t].id[s];
+          if (idx_state) idx_state[((size_t)b * N + i) * k1 + s] = top[t].id[s];
+        }
+      }
+    }
+  }
+}
+
+// Seeds for the small-cloud kernel.  One CTA per cloud sorts the cloud along a Z-order (Morton) curve in shared memory
+// -- bounding box, 12-bit Morton cell of every point (16 cells per axis), counting sort by cell -- and every query takes
+// the k1-th smallest distance over the `win` points around its own position in that order (itself included),
+// evaluated with the main kernel's exact arithmetic.  Those are real candidates, hence an exact upper bound on the
+// query's k1-th distance (nudged one ulp so that the strict '<' of the filter keeps ties); a window in Z-order adapts
+// to the local density, where a fixed neighbourhood of grid cells is empty in the tails of a cloud and crowded at its
+// centre.  Any bound would be CORRECT -- the main kernel drains early when a bound is loose -- a good one keeps it fast.
+constexpr int kMortonBits = 4, kMortonCells = 1 << (3 * kMortonBits);
+
+__device__ __forceinline__ int morton3_4bit(int x, int y, int z) {
+  auto spread = [](int v) { return (v & 1) | ((v & 2) << 2) | ((v & 4) << 4) | ((v & 8) << 6); };
+  return spread(x) | (spread(y) << 1) | (spread(z) << 2);
+}
+
+template <int KM>
+__global__ void __launch_bounds__(256) knn_seed_small_kernel(const float *__restrict__ pc, int N, int k1, int win,
+                                                             float *__restrict__ thr0, float *__restrict__ sbound) {
+  extern __shared__ float4 spts[];                   // [N] (x, y, z, xx) in Z-order
+  int *sidx = reinterpret_cast<int *>(spts + N);     // [N] original index of the point at each sorted position
+  int *scr = sidx + N;                               // [N] cell | rank-within-cell << 12
+  __shared__ int soff[kMortonCells + 1];
+  __shared__ float sred[6][8];
+  __shared__ float sbox[6];
+  __shared__ int swsum[8];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float *p = pc + (size_t)b * N * 3;
+
+  float lo[3] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F}, hi[3] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
+  for (int i = tid; i < N; i += 256)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float v = __ldg(p + (size_t)i * 3 + c);
+      lo[c] = fminf(lo[c], v);
+      hi[c] = fmaxf(hi[c], v);
+    }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    lo[c] = hg_warp_min_f32(lo[c]);
+    hi[c] = hg_warp_max_f32(hi[c]);
+  }
+  if (lane == 0)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      sred[c][warp] = lo[c];
+      sred[3 + c][warp] = hi[c];
+    }
+  for (int c = tid; c <= kMortonCells; c += 256) soff[c] = 0;
+  __syncthreads();
+  if (tid < 6) {
+    float v = sred[tid][0];
+    for (int w = 1; w < 8; ++w) v = tid < 3 ? fminf(v, sred[tid][w]) : fmaxf(v, sred[tid][w]);
+    sbox[tid] = v;
+  }
+  __syncthreads();
+  float mn[3], inv[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    mn[c] = sbox[c];
+    const float ext = sbox[3 + c] - mn[c];
+    inv[c] = (ext > 0.f && ext < CUDART_INF_F) ? (float)(1 << kMortonBits) / ext : 0.f;
+  }
+  if (tid == 0) {  // upper bound on max |p|^2 (farthest bounding-box corner), for the folded filter's slack
+    float sb = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) sb += fmaxf(sbox[c] * sbox[c], sbox[3 + c] * sbox[3 + c]);
+    sbound[(size_t)b * 8] = sb * 1.0001f;
+  }
+  for (int i = tid; i < N; i += 256) {
+    int cc[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float f = (__ldg(p + (size_t)i * 3 + c) - mn[c]) * inv[c];
+      cc[c] = (f == f) ? min(max((int)f, 0), (1 << kMortonBits) - 1) : 0;
+    }
+    const int cell = morton3_4bit(cc[0], cc[1], cc[2]);
+    const int rank = atomicAdd(&soff[cell], 1);  // order within a cell is irrelevant to a k-th smallest VALUE
+    scr[i] = cell | (rank << 12);
+  }
+  __syncthreads();
+  {  // exclusive scan of the 4096 cell counts: 16 consecutive cells per thread, then a block scan of the thread sums
+    constexpr int per = kMortonCells / 256;
+    int cnt[per], sum = 0;
+#pragma unroll
+    for (int c = 0; c < per; ++c) {
+      cnt[c] = soff[tid * per + c];
+      sum += cnt[c];
+    }
+    int incl = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int o = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += o;
+    }
+    if (lane == 31) swsum[warp] = incl;
+    __syncthreads();
+    int base = 0;
+    for (int w = 0; w < warp; ++w) base += swsum[w];
+    int run = base + incl - sum;
+#pragma unroll
+    for (int c = 0; c < per; ++c) {
+      soff[tid * per + c] = run;
+      run += cnt[c];
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < N; i += 256) {
+    const float x = __ldg(p + (size_t)i * 3), y = __ldg(p + (size_t)i * 3 + 1), z = __ldg(p + (size_t)i * 3 + 2);
+    const int v = scr[i];
+    const int pos = soff[v & (kMortonCells - 1)] + (v >> 12);
+    spts[pos] = make_float4(x, y, z, hg_sumsq3_seq(x, y, z));
+    sidx[pos] = i;
+  }
+  __syncthreads();
+
+  // queries in Z-order: the windows of the 32 lanes of a warp overlap (consecutive shared-memory addresses)
+  for (int s = tid; s < N; s += 256) {
+    const float4 q = spts[s];
+    const float a0 = -2.0f * q.x, a1 = -2.0f * q.y, a2 = -2.0f * q.z, a3 = q.w;
+    float v[KM];
+#pragma unroll
+    for (int t = 0; t < KM; ++t) v[t] = CUDART_INF_F;
+    const int t0 = max(0, min(s - win / 2, N - win)), t1 = min(N, t0 + win);
+    for (int t = t0; t < t1; ++t) {
+      const float4 r = spts[t];
+      float d = knn_dist_exact<HG_KNN_FORM_EXPANDED>(a0, a1, a2, a3, r.x, r.y, r.z, r.w);
+#pragma unroll
+      for (int u = 0; u < KM; ++u) {  // v stays sorted ascending: each level keeps the smaller, passes the larger on
+        const float l = fminf(v[u], d);
+        d = fmaxf(v[u], d);
+        v[u] = l;
+      }
+    }
+    float bound = -CUDART_INF_F;  // v[k1-1] = the largest of the first k1 entries (v is ascending); written as a max
+#pragma unroll                    // so that the list stays in registers (a runtime index would move it to local memory)
+    for (int t = 0; t < KM; ++t)
+      if (t < k1) bound = fmaxf(bound, v[t]);
+    thr0[(size_t)b * N + sidx[s]] = (bound < CUDART_INF_F) ? nextafterf(bound, CUDART_INF_F) : CUDART_INF_F;
   }
 }
 
@@ -289,15 +595,15 @@ static int g_force_qt = 0, g_force_gp = 0;
 
 template <int FORM, int QT, int KM, typename IdxT>
 int launch_qt(const float *q, const float *r, int B, int Nq, int Nr, int k1, float *vals, IdxT *idx,
-              const float *thr0, const float *sbound, cudaStream_t stream) {
+              const float *thr0, const float *sbound, cudaStream_t stream, int *idx_state = nullptr) {
   dim3 grid((Nq + QT * kThreads - 1) / (QT * kThreads), B);
   const bool prof = hg_prof_begin(HG_PROF_KNN, stream);
   // 8 candidates per hit bit (512-candidate tiles) for long candidate lists, 4 (256) for short ones, where the
   // cheaper group re-evaluation in the drain outweighs the extra mask updates (measured cross-over ~2-4k)
   if (g_force_gp ? g_force_gp == 2 : Nr < 2048)
-    knn3_kernel<FORM, QT, KM, 2, IdxT><<<grid, kThreads, 0, stream>>>(q, r, Nq, Nr, k1, vals, idx, thr0, sbound);
+    knn3_kernel<FORM, QT, KM, 2, IdxT><<<grid, kThreads, 0, stream>>>(q, r, Nq, Nr, k1, vals, idx, thr0, sbound, idx_state);
   else
-    knn3_kernel<FORM, QT, KM, 4, IdxT><<<grid, kThreads, 0, stream>>>(q, r, Nq, Nr, k1, vals, idx, thr0, sbound);
+    knn3_kernel<FORM, QT, KM, 4, IdxT><<<grid, kThreads, 0, stream>>>(q, r, Nq, Nr, k1, vals, idx, thr0, sbound, idx_state);
   hg_prof_end(HG_PROF_KNN, stream, prof);
   HG_CHECK_LAUNCH("knn3_kernel");
   return HG_OK;
@@ -305,7 +611,7 @@ int launch_qt(const float *q, const float *r, int B, int Nq, int Nr, int k1, flo
 
 template <int FORM, typename IdxT>
 int launch_form(const float *q, const float *r, int B, int Nq, int Nr, int k1, float *vals, IdxT *idx,
-                const float *thr0, const float *sbound, cudaStream_t stream) {
+                const float *thr0, const float *sbound, cudaStream_t stream, int *idx_state = nullptr) {
   if (k1 < 1 || k1 > 32) {
     hg_set_error("knn: k=%d outside [1,32]", k1);
     return HG_E_UNSUPPORTED;
@@ -319,30 +625,30 @@ int launch_form(const float *q, const float *r, int B, int Nq, int Nr, int k1, f
   const bool short_list = Nr < 2048;
   if (g_force_qt) {
     const int qt = g_force_qt;
-    if (k1 <= 6 && qt == 4) return launch_qt<FORM, 4, 6, IdxT>(q, r, B, Nq, Nr, k1, vals, idx, thr0, sbound, stream);
-    if (k1 <= 6 && qt == 2) return launch_qt<FORM, 2, 6, IdxT>(q, r, B, Nq, Nr, k1, vals, idx, thr0, sbound, stream);
-    if (k1 <= 6 && qt == 1) return launch_qt<FORM, 1, 6, IdxT>(q, r, B, Nq, Nr, k1, vals, idx, thr0, sbound, stream);
+    if (k1 <= 6 && qt == 4) return launch_qt<FORM, 4, 6, IdxT>(q, r, B, Nq, Nr, k1, vals, idx, thr0, sbound, stream, idx_state);
+    if (k1 <= 6 && qt == 2) return launch_qt<FORM, 2, 6, IdxT>(q, r, B, Nq, Nr, k1, vals, idx, thr0, sbound, stream, idx_state);
+    if (k1 <= 6 && qt == 1) return launch_qt<FORM, 1, 6, IdxT>(q, r, B, Nq, Nr, k1, vals, idx, thr0, sbound, stream, idx_state);
     if (k1 > 6 && k1 <= 20 && qt == 2)
-      return launch_qt<FORM, 2, 20, IdxT>(q, r, B, Nq, Nr, k1, vals, idx, thr0, sbound, stream);
+      return launch_qt<FORM, 2, 20, IdxT>(q, r, B, Nq, Nr, k1, vals, idx, thr0, sbound, stream, idx_state);
     if (k1 > 6 && k1 <= 20 && qt == 1)
-      return launch_qt<FORM, 1, 20, IdxT>(q, r, B, Nq, Nr, k1, vals, idx, thr0, sbound, stream);
-    if (k1 > 20 && qt == 1) return launch_qt<FORM, 1, 32, IdxT>(q, r, B, Nq, Nr, k1, vals, idx, thr0, sbound, stream);
+      return launch_qt<FORM, 1, 20, IdxT>(q, r, B, Nq, Nr, k1, vals, idx, thr0, sbound, stream, idx_state);
+    if (k1 > 20 && qt == 1) return launch_qt<FORM, 1, 32, IdxT>(q, r, B, Nq, Nr, k1, vals, idx, thr0, sbound, stream, idx_state);
     hg_set_error("knn: forced QT=%d has no instantiation for k=%d", qt, k1);
     return HG_E_UNSUPPORTED;
   }
   if (k1 <= 6) {
     if (!short_list && Nq >= 3 * kThreads && ctas(4) >= want)
-      return launch_qt<FORM, 4, 6, IdxT>(q, r, B, Nq, Nr, k1, vals, idx, thr0, sbound, stream);
+      return launch_qt<FORM, 4, 6, IdxT>(q, r, B, Nq, Nr, k1, vals, idx, thr0, sbound, stream, idx_state);
     if (Nq > kThreads && ctas(2) >= want)
-      return launch_qt<FORM, 2, 6, IdxT>(q, r, B, Nq, Nr, k1, vals, idx, thr0, sbound, stream);
-    return launch_qt<FORM, 1, 6, IdxT>(q, r, B, Nq, Nr, k1, vals, idx, thr0, sbound, stream);
+      return launch_qt<FORM, 2, 6, IdxT>(q, r, B, Nq, Nr, k1, vals, idx, thr0, sbound, stream, idx_state);
+    return launch_qt<FORM, 1, 6, IdxT>(q, r, B, Nq, Nr, k1, vals, idx, thr0, sbound, stream, idx_state);
   }
   if (k1 <= 20) {
     if (!short_list && Nq > kThreads && ctas(2) >= want)
-      return launch_qt<FORM, 2, 20, IdxT>(q, r, B, Nq, Nr, k1, vals, idx, thr0, sbound, stream);
-    return launch_qt<FORM, 1, 20, IdxT>(q, r, B, Nq, Nr, k1, vals, idx, thr0, sbound, stream);
+      return launch_qt<FORM, 2, 20, IdxT>(q, r, B, Nq, Nr, k1, vals, idx, thr0, sbound, stream, idx_state);
+    return launch_qt<FORM, 1, 20, IdxT>(q, r, B, Nq, Nr, k1, vals, idx, thr0, sbound, stream, idx_state);
   }
-  return launch_qt<FORM, 1, 32, IdxT>(q, r, B, Nq, Nr, k1, vals, idx, thr0, sbound, stream);
+  return launch_qt<FORM, 1, 32, IdxT>(q, r, B, Nq, Nr, k1, vals, idx, thr0, sbound, stream, idx_state);
 }
 
 // ---- threshold seeding for self-kNN ---------------------------------------------------------------------------
@@ -525,6 +831,165 @@ __global__ void __launch_bounds__(256) knn_bound_kernel(const float *__restrict_
   }
 }
 
+// Temporal seeds (attack loops call KNNDist thousands of times on a slowly moving cloud, CW/kNN.py:77-111): the
+// k1 neighbours a query had on the previous call, re-evaluated at the CURRENT coordinates with the main kernel's exact
+// arithmetic, are k1 distinct real candidates, so the largest of their distances is an exact upper bound on the
+// query's k1-th distance -- k1 evaluations per query instead of a spatial pre-pass, and a bound that is nearly tight.
+// The saved indices are only trusted after checking them: out of range or repeated entries give an infinite bound for
+// that query (it is then handled like an unseeded one), never a wrong result.  One CTA per cloud; also produces the
+// bound on max |p|^2 the folded filter needs.
+template <int KM>
+__global__ void __launch_bounds__(256) knn_seed_prev_kernel(const float *__restrict__ pc, int N, int k1,
+                                                            const int *__restrict__ prev /*[B,N,k1]*/,
+                                                            float *__restrict__ thr0, float *__restrict__ sbound) {
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const float *p = pc + (size_t)b * N * 3;
+  __shared__ float red[8];
+  float m = 0.f;
+  for (int i = tid; i < N; i += 256) {
+    const float x = __ldg(p + (size_t)i * 3), y = __ldg(p + (size_t)i * 3 + 1), z = __ldg(p + (size_t)i * 3 + 2);
+    m = fmaxf(m, fmaf(z, z, fmaf(y, y, x * x)));
+    const float a0 = -2.0f * x, a1 = -2.0f * y, a2 = -2.0f * z, a3 = hg_sumsq3_seq(x, y, z);
+    const int *pi = prev + ((size_t)b * N + i) * k1;
+    int id[KM];
+    float bound = -CUDART_INF_F;
+    bool ok = true;
+#pragma unroll
+    for (int t = 0; t < KM; ++t) {
+      id[t] = -1 - t;
+      if (t < k1) {
+        const int j = __ldg(pi + t);
+        id[t] = j;
+        if (j < 0 || j >= N) {
+          ok = false;
+        } else {
+          const float cx = __ldg(p + (size_t)j * 3), cy = __ldg(p + (size_t)j * 3 + 1), cz = __ldg(p + (size_t)j * 3 + 2);
+          bound = fmaxf(bound, knn_dist_exact<HG_KNN_FORM_EXPANDED>(a0, a1, a2, a3, cx, cy, cz, hg_sumsq3_seq(cx, cy, cz)));
+        }
+      }
+    }
+#pragma unroll
+    for (int t = 1; t < KM; ++t)
+#pragma unroll
+      for (int u = 0; u < t; ++u) ok = ok && (id[t] != id[u]);
+    thr0[(size_t)b * N + i] = (ok && bound < CUDART_INF_F) ? nextafterf(bound, CUDART_INF_F) : CUDART_INF_F;
+  }
+  m = hg_warp_max_f32(m);
+  if ((tid & 31) == 0) red[tid >> 5] = m;
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w]);
+    sbound[(size_t)b * 8] = m * 1.0001f;
+  }
+}
+
+int launch_seed_prev(const float *pc, int B, int N, int k1, const int *prev, float *thr0, float *sbound,
+                     cudaStream_t stream) {
+  if (k1 <= 6)
+    knn_seed_prev_kernel<6><<<B, 256, 0, stream>>>(pc, N, k1, prev, thr0, sbound);
+  else if (k1 <= 20)
+    knn_seed_prev_kernel<20><<<B, 256, 0, stream>>>(pc, N, k1, prev, thr0, sbound);
+  else
+    knn_seed_prev_kernel<32><<<B, 256, 0, stream>>>(pc, N, k1, prev, thr0, sbound);
+  HG_CHECK_LAUNCH("knn_seed_prev_kernel");
+  return HG_OK;
+}
+
+// ---- host side of the small-cloud path ---------------------------------------------------------------------
+static int g_small_max_n = 0;  // benchmark-only: largest cloud that takes the small-cloud path (0 = default)
+
+template <int QT, int KM, int GP>
+int launch_small(const float *pc, int B, int N, int k1, float *vals, int *idx, const float *thr0, const float *sbound,
+                 cudaStream_t stream, int *idx_state) {
+  const int W = ((N + 1) / 2 + 32 * GP - 1) / (32 * GP);
+  if (W > 32) {
+    hg_set_error("knn (small-cloud path): N=%d needs %d mask words with GP=%d (max 32)", N, W, GP);
+    return HG_E_UNSUPPORTED;
+  }
+  const size_t smem = (size_t)W * 32 * GP * 2 * sizeof(float4) + (size_t)QT * W * kThreads * sizeof(unsigned);
+  if (smem > 48 * 1024)
+    HG_CUDA(cudaFuncSetAttribute(knn3_small_kernel<QT, KM, GP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((N + QT * kThreads - 1) / (QT * kThreads), B);
+  const bool prof = hg_prof_begin(HG_PROF_KNN, stream);
+  knn3_small_kernel<QT, KM, GP><<<grid, kThreads, smem, stream>>>(pc, N, k1, W, vals, idx, thr0, sbound, idx_state);
+  hg_prof_end(HG_PROF_KNN, stream, prof);
+  HG_CHECK_LAUNCH("knn3_small_kernel");
+  return HG_OK;
+}
+
+template <int QT, int KM>
+int launch_small_gp(int gp, const float *pc, int B, int N, int k1, float *vals, int *idx, const float *thr0,
+                    const float *sbound, cudaStream_t stream, int *idx_state) {
+  if (gp == 1) return launch_small<QT, KM, 1>(pc, B, N, k1, vals, idx, thr0, sbound, stream, idx_state);
+  if (gp == 2) return launch_small<QT, KM, 2>(pc, B, N, k1, vals, idx, thr0, sbound, stream, idx_state);
+  return launch_small<QT, KM, 4>(pc, B, N, k1, vals, idx, thr0, sbound, stream, idx_state);
+}
+
+int knn3_small_main(const float *pc, int B, int N, int k1, float *vals, int *idx, const float *thr0, const float *sbound,
+                    cudaStream_t stream, int *idx_state);
+
+// self-kNN of clouds that fit in shared memory: seeds (one CTA per cloud), then the deferred-drain kernel.
+// workspace: thr0 [B,N] floats, then sbound [B] stride 8.
+int knn3_small_self(const float *pc, int B, int N, int k1, float *vals, int *idx, float *thr0, float *sbound,
+                    cudaStream_t stream, int *idx_state, bool state_valid) {
+  if (idx_state && state_valid) {
+    int rc = launch_seed_prev(pc, B, N, k1, idx_state, thr0, sbound, stream);
+    if (rc) return rc;
+    return knn3_small_main(pc, B, N, k1, vals, idx, thr0, sbound, stream, idx_state);
+  }
+  const size_t seed_smem = (size_t)N * (sizeof(float4) + 2 * sizeof(int));
+  // window of the Z-order scan: enough points for a k1-th smallest that is close to the true one
+  const int win = k1 <= 8 ? 32 : (k1 <= 16 ? 48 : 64);
+  static bool attr_set[3] = {false, false, false};
+  constexpr int kSeedMaxSmem = 8192 * (int)(sizeof(float4) + 2 * sizeof(int));
+  if (k1 <= 6) {
+    if (!attr_set[0]) {
+      HG_CUDA(cudaFuncSetAttribute(knn_seed_small_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSeedMaxSmem));
+      attr_set[0] = true;
+    }
+    knn_seed_small_kernel<6><<<B, 256, seed_smem, stream>>>(pc, N, k1, win, thr0, sbound);
+  } else if (k1 <= 20) {
+    if (!attr_set[1]) {
+      HG_CUDA(cudaFuncSetAttribute(knn_seed_small_kernel<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSeedMaxSmem));
+      attr_set[1] = true;
+    }
+    knn_seed_small_kernel<20><<<B, 256, seed_smem, stream>>>(pc, N, k1, win, thr0, sbound);
+  } else {
+    if (!attr_set[2]) {
+      HG_CUDA(cudaFuncSetAttribute(knn_seed_small_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSeedMaxSmem));
+      attr_set[2] = true;
+    }
+    knn_seed_small_kernel<32><<<B, 256, seed_smem, stream>>>(pc, N, k1, win, thr0, sbound);
+  }
+  HG_CHECK_LAUNCH("knn_seed_small_kernel");
+  return knn3_small_main(pc, B, N, k1, vals, idx, thr0, sbound, stream, idx_state);
+}
+
+int knn3_small_main(const float *pc, int B, int N, int k1, float *vals, int *idx, const float *thr0, const float *sbound,
+                    cudaStream_t stream, int *idx_state) {
+  // Queries per lane / candidate pairs per filter bit (tools/knn_small_sweep.py, B200): two queries per lane amortise
+  // the broadcast candidate loads, more would lengthen the serial drains; one pair per bit makes the drain's group
+  // re-evaluation cheapest, but needs N/64 mask words per query, which costs occupancy beyond ~1.3k points.
+  int gp = g_force_gp ? g_force_gp : (N <= 1280 ? 1 : 2);
+  if (N > 2048 && gp < 2) gp = 2;
+  if (N > 4096 && gp < 4) gp = 4;
+  int qt = g_force_qt ? g_force_qt : 2;
+  if (k1 <= 6) {
+    if (qt == 4) return launch_small_gp<4, 6>(gp, pc, B, N, k1, vals, idx, thr0, sbound, stream, idx_state);
+    if (qt == 2) return launch_small_gp<2, 6>(gp, pc, B, N, k1, vals, idx, thr0, sbound, stream, idx_state);
+    if (qt == 1) return launch_small_gp<1, 6>(gp, pc, B, N, k1, vals, idx, thr0, sbound, stream, idx_state);
+  } else if (k1 <= 20) {
+    if (!g_force_qt) qt = 1;
+    if (qt == 2) return launch_small_gp<2, 20>(gp, pc, B, N, k1, vals, idx, thr0, sbound, stream, idx_state);
+    if (qt == 1) return launch_small_gp<1, 20>(gp, pc, B, N, k1, vals, idx, thr0, sbound, stream, idx_state);
+  } else {
+    if (!g_force_qt) qt = 1;
+    if (qt == 1) return launch_small_gp<1, 32>(gp, pc, B, N, k1, vals, idx, thr0, sbound, stream, idx_state);
+  }
+  hg_set_error("knn: forced QT=%d has no instantiation for k=%d", qt, k1);
+  return HG_E_UNSUPPORTED;
+}
+
 int seed_grid(int N) {
   int G = (int)lroundf(cbrtf((float)N / 3.0f));
   if (G < 1) G = 1;
@@ -568,18 +1033,30 @@ HG_API void hg_knn_force_shape(int qt, int gp) {
   g_force_gp = gp;
 }
 
-// self-kNN (expanded form) with grid-seeded thresholds; falls back to the unseeded launch for small clouds
+HG_API void hg_knn_tune_small(int small_max_n) { g_small_max_n = small_max_n; }
+
+// self-kNN (expanded form) with seeded thresholds; falls back to the unseeded launch when there is no workspace.
+// idx_state (optional, [B,N,k1]): the neighbour indices of the previous call on a nearby cloud -- read as temporal
+// seeds when state_valid, and overwritten with this call's indices (a second copy of idx).
 int hg_knn3_self_seeded_i32(const float *pc, int B, int N, int k1, float *vals, int *idx, void *workspace,
-                            size_t workspace_bytes, cudaStream_t stream) {
+                            size_t workspace_bytes, cudaStream_t stream, int *idx_state, int state_valid) {
   if (k1 > 32 || workspace == nullptr || workspace_bytes < hg_knn3_seed_workspace_bytes(B, N))
-    return launch_form<HG_KNN_FORM_EXPANDED, int>(pc, pc, B, N, N, k1, vals, idx, nullptr, nullptr, stream);
+    return launch_form<HG_KNN_FORM_EXPANDED, int>(pc, pc, B, N, N, k1, vals, idx, nullptr, nullptr, stream, idx_state);
+  float *sb_slot = (float *)((char *)workspace + hg_align((size_t)B * N * sizeof(int)));  // `params`: [B] stride 8
+  float *thr_slot = (float *)((char *)sb_slot + hg_align((size_t)B * 8 * sizeof(float)));  // `thr0`: [B,N]
+  const int small_max = g_small_max_n > 0 ? (g_small_max_n < 8192 ? g_small_max_n : 8192) : (g_small_max_n < 0 ? -1 : 2047);
+  if (N <= small_max)  // clouds that fit in shared memory: deferred-drain kernel
+    return knn3_small_self(pc, B, N, k1, vals, idx, thr_slot, sb_slot, stream, idx_state, state_valid != 0);
+  if (idx_state && state_valid) {  // temporal seeds instead of the grid pre-pass
+    int rc = launch_seed_prev(pc, B, N, k1, idx_state, thr_slot, sb_slot, stream);
+    if (rc) return rc;
+    return launch_form<HG_KNN_FORM_EXPANDED_FOLD4, int>(pc, pc, B, N, N, k1, vals, idx, thr_slot, sb_slot, stream, idx_state);
+  }
   if (N < (g_seed_min_n > 0 ? g_seed_min_n : 2048)) {
-    // small clouds: cold thresholds (the grid pre-pass costs more than the insertions it saves, measured below
-    // ~2k points), but still the 4-operation folded filter -- it only needs a bound on max |p|^2
-    float *sb = (float *)((char *)workspace + hg_align((size_t)B * N * sizeof(int)));  // the `params` slot
-    knn_bound_kernel<<<B, 256, 0, stream>>>(pc, N, sb);
+    // (benchmark-only, when the small-cloud path is switched off) cold thresholds with the 4-operation folded filter
+    knn_bound_kernel<<<B, 256, 0, stream>>>(pc, N, sb_slot);
     HG_CHECK_LAUNCH("knn_bound_kernel");
-    return launch_form<HG_KNN_FORM_EXPANDED_FOLD4, int>(pc, pc, B, N, N, k1, vals, idx, nullptr, sb, stream);
+    return launch_form<HG_KNN_FORM_EXPANDED_FOLD4, int>(pc, pc, B, N, N, k1, vals, idx, nullptr, sb_slot, stream, idx_state);
   }
   const int G = seed_grid(N), ncell = G * G * G;
   char *w = (char *)workspace;
@@ -617,5 +1094,5 @@ int hg_knn3_self_seeded_i32(const float *pc, int B, int N, int k1, float *vals, 
     knn_seed_kernel<32><<<grid, 128, 0, stream>>>(sorted, N, G, params, csr.off, csr.list, thr0, near8);
   HG_CHECK_LAUNCH("knn_seed_kernel");
   // seeded path: the bounding box is known, so the main loop can run the 4-operation folded filter
-  return launch_form<HG_KNN_FORM_EXPANDED_FOLD4, int>(pc, pc, B, N, N, k1, vals, idx, thr0, params + 6, stream);
+  return launch_form<HG_KNN_FORM_EXPANDED_FOLD4, int>(pc, pc, B, N, N, k1, vals, idx, thr0, params + 6, stream, idx_state);
 }

@@ -26,6 +26,7 @@ _SIGNATURES = {
     "hg_nn_bidir_tune": (None, [I, I]),
     "hg_knn_tune": (None, [I, I]),
     "hg_knn_force_shape": (None, [I, I]),
+    "hg_knn_tune_small": (None, [I]),
     "hg_launch_count": (ctypes.c_ulonglong, []),
     "hg_prof_enable": (None, [I]),
     "hg_prof_read": (I, [I, ctypes.POINTER(F), ctypes.POINTER(I)]),
@@ -35,6 +36,7 @@ _SIGNATURES = {
     "hg_set_loss_bwd_f32": (I, [P, P, P, P, P, P, P, P, I, I, I, I, I, P, P, P, Z, P]),
     "hg_knn_self_workspace_bytes": (Z, [I, I, I, I]),
     "hg_knn_self_f32": (I, [P, I, I, I, I, P, P, P, Z, P]),
+    "hg_knn_self_temporal_f32": (I, [P, I, I, I, I, P, P, P, I, P, Z, P]),
     "hg_knn_outlier_fwd_f32": (I, [P, I, I, I, F, P, P, P, P, P]),
     "hg_knn_outlier_bwd_workspace_bytes": (Z, [I, I, I]),
     "hg_knn_outlier_bwd_f32": (I, [P, P, P, P, I, I, I, I, P, P, Z, P]),

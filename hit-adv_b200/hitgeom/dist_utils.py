@@ -74,17 +74,37 @@ class HausdorffDist(nn.Module):
 
 
 class KNNDist(nn.Module):
+    """Same constructor as the reference.  `temporal_seeds(True)` (an addition) keeps the neighbour indices of the
+    previous call as state and hands them to the next call as seeds: inside an attack loop (CW/kNN.py:77-111) the cloud
+    moves by a learning-rate step per iteration, so they bound every k-th distance almost tightly and replace the
+    spatial pre-pass.  The loss and its gradient are the same bits either way; the state is per (batch shape, device)
+    and replay-safe (the kernel updates it in place)."""
+
     def __init__(self, k=5, alpha=1.05):
         super(KNNDist, self).__init__()
         self.k = k
         self.alpha = alpha
+        self.temporal = False
+        self._state = {}
+
+    def temporal_seeds(self, on=True):
+        self.temporal = bool(on)
+        self._state.clear()
+        return self
 
     def forward(self, pc, weights=None, batch_avg=True):
         """pc: [B, K, 3] or [B, 3, K] (dist_utils.py:145-147 treats shape[1] == 3 as channel-first)."""
         B = pc.shape[0]
         if pc.shape[1] == 3:
             pc = pc.transpose(2, 1)  # kernels are point-major
-        loss = F.knn_outlier_loss(pc, self.k, self.alpha)  # [B]
+        state, valid = None, False
+        if self.temporal and pc.is_cuda and pc.shape[2] == 3:
+            key = (tuple(pc.shape), pc.device)
+            valid = key in self._state
+            if not valid:
+                self._state[key] = torch.empty((pc.shape[0], pc.shape[1], self.k + 1), dtype=torch.int32, device=pc.device)
+            state = self._state[key]
+        loss = F.knn_outlier_loss(pc, self.k, self.alpha, state, valid)  # [B]
         return _finish(loss, _weights(weights, B, loss.device), batch_avg)
 
 
@@ -95,6 +115,11 @@ class ChamferkNNDist(nn.Module):
         self.knn_dist = KNNDist(k=knn_k, alpha=knn_alpha)
         self.w1 = chamfer_weight
         self.w2 = knn_weight
+
+    def temporal_seeds(self, on=True):
+        """See KNNDist.temporal_seeds."""
+        self.knn_dist.temporal_seeds(on)
+        return self
 
     def forward(self, adv_pc, ori_pc, weights=None, batch_avg=True):
         chamfer_loss = self.chamfer_dist(adv_pc, ori_pc, weights=weights, batch_avg=batch_avg)

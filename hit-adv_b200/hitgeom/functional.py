@@ -157,18 +157,24 @@ def hausdorff_losses(preds, gts):
 # ------------------------------------------------------------------------------------------------------------
 # kNN (util/dist_utils.py KNNDist, model/dgcnn_cls.py knn, pytorch3d.ops.knn_points)
 # ------------------------------------------------------------------------------------------------------------
-def knn_self(pc, k1, want_vals=True):
+def knn_self(pc, k1, want_vals=True, state=None, state_valid=False):
     """k1 smallest per row of dist[i,j] = (xx_j + (-2 zz_ij)) + xx_i.  pc [B,K,C] point-major.
 
-    Returns (vals [B,K,k1] ascending or None, idx [B,K,k1] int32)."""
+    Returns (vals [B,K,k1] ascending or None, idx [B,K,k1] int32).  `state` (optional int32 [B,K,k1], caller-owned):
+    the indices of an earlier call on a nearby cloud, used as temporal seeds when `state_valid`, and overwritten with
+    this call's indices (hg_knn_self_temporal_f32); the results do not depend on it."""
     require(pc, "pc", ndim=3)
     B, K, C = pc.shape
     dev = pc.device
     vals = torch.empty((B, K, k1), dtype=torch.float32, device=dev) if want_vals else None
     idx = torch.empty((B, K, k1), dtype=torch.int32, device=dev)
     ws = workspace(lib().hg_knn_self_workspace_bytes(B, K, C, k1), dev)
-    check(lib().hg_knn_self_f32(ptr(pc), B, K, C, k1, ptr(vals), ptr(idx), ptr(ws), ws.numel(), stream_ptr()),
-          "hg_knn_self_f32")
+    if state is not None:
+        require(state, "state", dtype=torch.int32, ndim=3)
+        if tuple(state.shape) != (B, K, k1) or state.device != dev:
+            raise RuntimeError(f"state must be an int32 [{B},{K},{k1}] tensor on {dev}")
+    check(lib().hg_knn_self_temporal_f32(ptr(pc), B, K, C, k1, ptr(vals), ptr(idx), ptr(state), 1 if state_valid else 0,
+                                         ptr(ws), ws.numel(), stream_ptr()), "hg_knn_self_temporal_f32")
     return vals, idx
 
 
@@ -176,11 +182,11 @@ class KnnOutlierFn(torch.autograd.Function):
     """pc [B,K,3] point-major -> per-sample kNN-outlier loss [B] (dist_utils.py:148-167, unit weights)."""
 
     @staticmethod
-    def forward(ctx, pc, k, alpha):
+    def forward(ctx, pc, k, alpha, state=None, state_valid=False):
         pc_c = pc.detach().contiguous()
         B, K, C = pc_c.shape
         dev = pc_c.device
-        vals, idx = knn_self(pc_c, k + 1)
+        vals, idx = knn_self(pc_c, k + 1, state=state, state_valid=state_valid)
         value = torch.empty((B, K), dtype=torch.float32, device=dev)
         mask = torch.empty((B, K), dtype=torch.float32, device=dev)
         loss = torch.empty(B, dtype=torch.float32, device=dev)
@@ -199,11 +205,11 @@ class KnnOutlierFn(torch.autograd.Function):
         ws = workspace(lib().hg_knn_outlier_bwd_workspace_bytes(B, K, ctx.k1), pc_c.device)
         check(lib().hg_knn_outlier_bwd_f32(ptr(pc_c), ptr(idx), ptr(mask), ptr(g), B, K, C, ctx.k1, ptr(grad), ptr(ws),
                                            ws.numel(), stream_ptr()), "hg_knn_outlier_bwd_f32")
-        return grad, None, None
+        return grad, None, None, None, None
 
 
-def knn_outlier_loss(pc, k, alpha):
-    return KnnOutlierFn.apply(_as_points(pc, "pc"), int(k), float(alpha))
+def knn_outlier_loss(pc, k, alpha, state=None, state_valid=False):
+    return KnnOutlierFn.apply(_as_points(pc, "pc"), int(k), float(alpha), state, bool(state_valid))
 
 
 def knn_points_raw(p1, p2, K):
@@ -353,6 +359,11 @@ def tune_nn_bidir(T=0, RB=0):
 def force_knn_shape(qt=0, gp=0):
     """Test-only override of the streaming kNN kernel's instantiation (queries per lane, pairs per filter bit)."""
     lib().hg_knn_force_shape(int(qt), int(gp))
+
+
+def tune_knn_small(small_max_n=0):
+    """Benchmark / test-only: largest cloud on the small-cloud kNN path (0 = default, negative = off)."""
+    lib().hg_knn_tune_small(int(small_max_n))
 
 
 __all__ = [n for n in dir() if not n.startswith("_")]

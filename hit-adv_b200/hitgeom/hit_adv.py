@@ -33,7 +33,11 @@ from .pytorch3d_ops import knn_gather, knn_points
 class HiT_ADV:
     def __init__(self, model, adv_func, attack_lr=1e-2, init_weight=10., max_weight=80., binary_step=10, num_iter=500,
                  clip_func=None, cd_weight=0, curv_weight=0, ker_weight=0, hide_weight=0, curv_loss_knn=32,
-                 central_num=32, total_central_num=128, max_sigm=0.7, min_sigm=0.1, budget=0.1, alpha=1):
+                 central_num=32, total_central_num=128, max_sigm=0.7, min_sigm=0.1, budget=0.1, alpha=1, graph=False):
+        # graph=True (not in the reference's signature): after three eager iterations of every binary step, the
+        # iteration is captured once and replayed as ONE CUDA-graph launch; Adam then keeps its step counter on the
+        # device (capturable), a 1e-7 relative difference in the step size against the Python-double bias corrections
+        self.graph = graph
         self.model = model.cuda()
         self.model.eval()
         self.adv_func = adv_func
@@ -56,6 +60,7 @@ class HiT_ADV:
         self.total_central_num = total_central_num
         self.iterations_run = 0  # inner iterations of the last attack() call (for the benchmark)
         self._loop_events = None
+        self._replay_events, self.replays = [], 0
 
     # ---- helpers (HiT_ADV.py:298-346) ---------------------------------------------------------------------------
     @staticmethod
@@ -170,61 +175,99 @@ class HiT_ADV:
         cd_weight = torch.ones(B, device=dev) * self.cd_weight
         o_bestdist = torch.full((B,), 1e10, device=dev)
         o_bestattack = torch.zeros((B, 3, K), device=dev)
-        tmp_adv_data = ori_data
-        dist_val = o_bestdist
         self.iterations_run = 0
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record()
+        # graph mode: everything from the parameter draws on runs on ONE side stream -- warm-up iterations, capture and
+        # replays -- so that the leaves' gradient accumulators live on the stream the capture uses (created on the
+        # legacy default stream by eager warm-up iterations, they would make the capture depend on it and abort)
+        caller_stream = torch.cuda.current_stream()
+        side = torch.cuda.Stream() if self.graph else caller_stream
+        side.wait_stream(caller_stream)
+        with torch.cuda.stream(side):
+            ev0.record()
 
-        for _binary_step in range(self.binary_step):
-            # same CPU-generator draws, in the same order, as HiT_ADV.py:130-134
-            perturb_mat = (torch.rand(B, J, 3) * torch.tensor(self.budget)).to(dev)
-            gauss_delta = (torch.ones((B, J)).to(dev) * self.min_sigm
-                           + torch.rand((B, J)).to(dev) * (self.max_sigm - self.min_sigm))
-            perturb_mat.requires_grad_()
-            gauss_delta.requires_grad_()
-            bestdist = torch.full((B,), 1e10, device=dev)
-            bestscore = torch.full((B,), -1, dtype=torch.long, device=dev)
-            opt = optim.Adam([{'params': perturb_mat, 'lr': self.attack_lr * 5},
-                              {'params': gauss_delta, 'lr': self.attack_lr * 3}], weight_decay=0.)
+            last_adv = ori_data.clone()
+            replay_ms, replays = [], 0
+            for _binary_step in range(self.binary_step):
+                # same CPU-generator draws, in the same order, as HiT_ADV.py:130-134
+                perturb_mat = (torch.rand(B, J, 3) * torch.tensor(self.budget)).to(dev)
+                gauss_delta = (torch.ones((B, J)).to(dev) * self.min_sigm
+                               + torch.rand((B, J)).to(dev) * (self.max_sigm - self.min_sigm))
+                perturb_mat.requires_grad_()
+                gauss_delta.requires_grad_()
+                bestdist = torch.full((B,), 1e10, device=dev)
+                bestscore = torch.full((B,), -1, dtype=torch.long, device=dev)
+                opt = optim.Adam([{'params': perturb_mat, 'lr': self.attack_lr * 5},
+                                  {'params': gauss_delta, 'lr': self.attack_lr * 3}], weight_decay=0.,
+                                 capturable=self.graph)
 
-            for _iteration in range(self.num_iter):
-                with torch.no_grad():
-                    perturb_mat.clamp_(min=-self.budget, max=self.budget)
-                    gauss_delta.clamp_(min=self.min_sigm, max=self.max_sigm)
-                loss, tmp_adv_data, logits = self._iteration_loss(ori_data, central_points, central_kappa_std, perturb_mat,
-                                                                  gauss_delta, target, scale_const, chamfer_dist, cd_weight)
+                def iteration():
+                    """One inner iteration (HiT_ADV.py:156-262) on static buffers: no host round trip, no allocation that
+                    outlives it -- replayable as one CUDA graph."""
+                    with torch.no_grad():
+                        perturb_mat.clamp_(min=-self.budget, max=self.budget)
+                        gauss_delta.clamp_(min=self.min_sigm, max=self.max_sigm)
+                    loss, tmp_adv_data, logits = self._iteration_loss(ori_data, central_points, central_kappa_std, perturb_mat,
+                                                                      gauss_delta, target, scale_const, chamfer_dist, cd_weight)
+                    with torch.no_grad():  # best-result bookkeeping, on the device
+                        pred = torch.argmax(logits, dim=1)
+                        dist_val = self.transformation_loss(tmp_adv_data, perturb_mat, gauss_delta, batch_avg=False)
+                        wrong = pred != target
+                        upd = wrong & (dist_val < bestdist)
+                        bestdist.copy_(torch.where(upd, dist_val, bestdist))
+                        bestscore.copy_(torch.where(upd, pred, bestscore))
+                        upd_o = wrong & (dist_val < o_bestdist)
+                        o_bestdist.copy_(torch.where(upd_o, dist_val, o_bestdist))
+                        o_bestattack.copy_(torch.where(upd_o[:, None, None], tmp_adv_data, o_bestattack))
+                        last_adv.copy_(tmp_adv_data)
+                    opt.zero_grad(set_to_none=False)
+                    loss.mean().backward()
+                    opt.step()
 
-                with torch.no_grad():  # best-result bookkeeping, on the device, no host round trip
-                    pred = torch.argmax(logits, dim=1)
-                    dist_val = self.transformation_loss(tmp_adv_data, perturb_mat, gauss_delta, batch_avg=False)
-                    wrong = pred != target
-                    upd = wrong & (dist_val < bestdist)
-                    bestdist = torch.where(upd, dist_val, bestdist)
-                    bestscore = torch.where(upd, pred, bestscore)
-                    upd_o = wrong & (dist_val < o_bestdist)
-                    o_bestdist = torch.where(upd_o, dist_val, o_bestdist)
-                    o_bestattack = torch.where(upd_o[:, None, None], tmp_adv_data, o_bestattack)
+                graph, warm = None, min(3, self.num_iter)
+                for _iteration in range(self.num_iter):
+                    if self.graph and _iteration == warm:
+                        # the warm-up iterations ran eagerly (allocator pools, Adam state); capture ONE iteration, replay it
+                        graph = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(graph, stream=side):
+                            iteration()
+                        eg0, eg1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        eg0.record()
+                    if graph is not None:  # (capture records the iteration without running it)
+                        graph.replay()
+                    else:
+                        iteration()
+                    self.iterations_run += 1
+                if graph is not None:
+                    eg1.record()
+                    replay_ms.append((eg0, eg1))
+                    replays += self.num_iter - warm
 
-                opt.zero_grad()
-                loss.mean().backward()
-                opt.step()
-                self.iterations_run += 1
+                with torch.no_grad():  # binary-search update of the per-sample weight (HiT_ADV.py:264-273), vectorised
+                    ok = (bestscore != target) & (bestscore != -1) & (bestdist <= o_bestdist)
+                    lower_bound = torch.where(ok, torch.maximum(lower_bound, scale_const), lower_bound)
+                    upper_bound = torch.where(ok, upper_bound, torch.minimum(upper_bound, scale_const))
+                    scale_const = (lower_bound + upper_bound) / 2.
 
-            with torch.no_grad():  # binary-search update of the per-sample weight (HiT_ADV.py:264-273), vectorised
-                ok = (bestscore != target) & (bestscore != -1) & (bestdist <= o_bestdist)
-                lower_bound = torch.where(ok, torch.maximum(lower_bound, scale_const), lower_bound)
-                upper_bound = torch.where(ok, upper_bound, torch.minimum(upper_bound, scale_const))
-                scale_const = (lower_bound + upper_bound) / 2.
-
-        ev1.record()
+            ev1.record()
+        caller_stream.wait_stream(side)
         with torch.no_grad():
             failed = lower_bound == 0.
-            o_bestattack = torch.where(failed[:, None, None], tmp_adv_data.detach(), o_bestattack)
+            o_bestattack = torch.where(failed[:, None, None], last_adv, o_bestattack)
             success_num = (lower_bound > 0.).sum()
         out = o_bestattack.transpose(1, 2).contiguous()
         self._loop_events = (ev0, ev1)
+        self._replay_events, self.replays = replay_ms, replays
         return out, success_num
+
+    @property
+    def replay_ms(self):
+        """Device time [ms] of the graph-replayed iterations of the last attack() call (graph=True), summed."""
+        total = 0.0
+        for e0, e1 in self._replay_events:
+            e1.synchronize()
+            total += e0.elapsed_time(e1)
+        return total
 
     @property
     def loop_ms(self):

@@ -61,6 +61,9 @@ void hg_knn_tune(int seed_min_n, int neighbourhood);
  * pairs per filter bit (2, 4); 0 = chosen from the problem size.  A combination that is not instantiated for the
  * requested k makes the next kNN call fail with HG_E_UNSUPPORTED.  Process-global, not thread-safe. */
 void hg_knn_force_shape(int qt, int gp);
+/* Benchmark / test-only: largest cloud whose self-kNN takes the small-cloud path (whole cloud resident in shared
+ * memory, drain deferred): 0 = default (2047 points), a negative value switches the path off, at most 8192. */
+void hg_knn_tune_small(int small_max_n);
 
 /* ---------------------------------------------------------------------------------------------------------
  * util/set_distance.py:15-32,45-48,65-68 -- `_Distance.batch_pairwise_dist` fused with the two `torch.min`
@@ -101,6 +104,15 @@ int hg_set_loss_bwd_f32(const float *gts, const float *preds, const int *arg1, c
 size_t hg_knn_self_workspace_bytes(int B, int K, int C, int k1);
 int hg_knn_self_f32(const float *pc, int B, int K, int C, int k1, float *vals, int *idx, void *workspace,
                     size_t workspace_bytes, hgStream stream);
+
+/* The same search inside an attack loop (CW/kNN.py:77-111 calls KNNDist on a slowly moving cloud 2500 times):
+ * idx_state [B,K,k1] is caller-owned state.  When state_valid != 0 it holds the neighbour indices an earlier call
+ * wrote for a NEARBY cloud of the same shape; re-evaluated at the current coordinates they bound every query's k1-th
+ * distance, which replaces the spatial pre-pass (C == 3; ignored otherwise).  The entries are checked (range,
+ * distinctness): garbage costs speed, never correctness -- results are identical to hg_knn_self_f32.  On return
+ * idx_state holds this call's indices (a copy of idx; idx_state may alias idx). */
+int hg_knn_self_temporal_f32(const float *pc, int B, int K, int C, int k1, float *vals, int *idx, int *idx_state,
+                             int state_valid, void *workspace, size_t workspace_bytes, hgStream stream);
 
 /* util/dist_utils.py:157-172: value = mean of the k = k1-1 non-first neighbours, threshold mean+alpha*std
  * (unbiased), mask, loss[b] = weights[b] * mean(value*mask).  weights may be NULL (ones). */

@@ -43,11 +43,12 @@ QT_FOR_K = {6: (1, 2, 4), 5: (1, 2, 4), 1: (4,), 20: (1, 2), 12: (2,), 32: (1,),
 
 
 @pytest.mark.parametrize("n", [2048, 1024, 3000, 333])
-@pytest.mark.parametrize("gp", [2, 4])
+@pytest.mark.parametrize("gp", [1, 2, 4])
 @pytest.mark.parametrize("k1", sorted(QT_FOR_K))
 def test_self_knn_every_forced_instantiation(oracle, F, n, gp, k1):
-    """Self-kNN (KNNDist, DGCNN layer 1): n >= 2048 takes the grid-seeded folded-filter path, n < 2048 the small-cloud
-    path; every QT the list length admits, both GP."""
+    """Self-kNN (KNNDist, DGCNN layer 1): n >= 2048 takes the grid-seeded streaming kernel (GP = 2 or 4; a forced 1
+    means 4 there), n < 2048 the small-cloud kernel (Z-order seeds, deferred drain; GP = 1, 2, 4); every QT the list
+    length admits."""
     for tag, pc in _inputs(n):
         ov, oi = oracle.knn_self(pc, k1, threads=oracle.host_threads())
         for qt in QT_FOR_K[k1]:
@@ -112,3 +113,53 @@ def test_big_batch_variants_selected_naturally(oracle, F, B, n, k1):
     ov, oi = oracle.knn_self(pc, k1, threads=oracle.host_threads())
     assert np.array_equal(vals.cpu().numpy(), ov)
     assert np.array_equal(idx.cpu().numpy(), oi)
+
+
+# ---- temporal seeds (hg_knn_self_temporal_f32): results never depend on the state ------------------------------------
+@pytest.mark.parametrize("n,k1", [(1024, 6), (700, 20), (2048, 6), (3000, 17), (40, 32)])
+def test_temporal_seeds_never_change_results(oracle, F, n, k1):
+    """State from a previous call on a nearby cloud, stale state, and garbage state (out of range, repeated entries,
+    all zeros): values and indices are the oracle's bit for bit, and the state ends up holding this call's indices."""
+    rng = np.random.default_rng(n + k1)
+    base = clouds(3, n, 50 + n, "surface")
+    base[2, : n // 4] = base[2, n // 4 : 2 * (n // 4)]
+    moved = (base + 2e-3 * rng.standard_normal(base.shape)).astype(np.float32)
+    ov0, oi0 = oracle.knn_self(base, k1, threads=3)
+    ov1, oi1 = oracle.knn_self(moved, k1, threads=3)
+    state = torch.empty((3, n, k1), dtype=torch.int32, device="cuda")
+    v, i = F.knn_self(gpu(base), k1, state=state, state_valid=False)  # first call: state is output only
+    assert np.array_equal(v.cpu().numpy(), ov0) and np.array_equal(i.cpu().numpy(), oi0)
+    assert torch.equal(state, i)
+    v, i = F.knn_self(gpu(moved), k1, state=state, state_valid=True)  # seeds = neighbours of the previous cloud
+    assert np.array_equal(v.cpu().numpy(), ov1) and np.array_equal(i.cpu().numpy(), oi1)
+    assert torch.equal(state, i)
+    for tag, junk in (("out of range", rng.integers(-5, 2 * n, size=(3, n, k1))),
+                      ("repeated", np.repeat(rng.integers(0, n, size=(3, n, 1)), k1, axis=2)),
+                      ("zeros", np.zeros((3, n, k1))),
+                      ("far neighbours", rng.permuted(np.tile(np.arange(n), (3, 1)), axis=1)[:, :, None]
+                       + np.arange(k1)[None, None, :] * 0 + rng.integers(0, n, size=(3, n, k1)))):
+        st = torch.from_numpy(np.ascontiguousarray(junk % (4 * n) - (n if tag == "out of range" else 0)).astype(np.int32)).cuda()
+        v, i = F.knn_self(gpu(moved), k1, state=st, state_valid=True)
+        assert np.array_equal(v.cpu().numpy(), ov1), (tag, "values")
+        assert np.array_equal(i.cpu().numpy(), oi1), (tag, "indices")
+        assert torch.equal(st, i), tag
+
+
+def test_knndist_temporal_state_same_bits_as_stateless():
+    """KNNDist with temporal seeds inside a (mock) attack loop: loss and gradient bit-identical to the stateless module."""
+    from hitgeom.dist_utils import KNNDist
+
+    a, b = KNNDist(k=5), KNNDist(k=5).temporal_seeds(True)
+    x = gpu(clouds(4, 1024, 9)).requires_grad_()
+    y = x.detach().clone().requires_grad_()
+    for step in range(4):
+        la = a(x, batch_avg=False)
+        la.sum().backward()
+        lb = b(y, batch_avg=False)
+        lb.sum().backward()
+        assert torch.equal(la, lb) and torch.equal(x.grad, y.grad), step
+        with torch.no_grad():
+            x -= 0.5 * x.grad
+            y -= 0.5 * y.grad
+        x.grad = None
+        y.grad = None
