@@ -98,7 +98,9 @@ class KNNDist(nn.Module):
         if pc.shape[1] == 3:
             pc = pc.transpose(2, 1)  # kernels are point-major
         state, valid = None, False
-        if self.temporal and pc.is_cuda and pc.shape[2] == 3:
+        # (getattr: install.patch_reference() binds this forward to the REFERENCE's KNNDist class, whose __init__ knows
+        # nothing of the temporal state)
+        if getattr(self, "temporal", False) and pc.is_cuda and pc.shape[2] == 3:
             key = (tuple(pc.shape), pc.device)
             valid = key in self._state
             if not valid:
