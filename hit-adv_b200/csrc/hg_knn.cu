@@ -306,8 +306,9 @@ __global__ void __launch_bounds__(256) knn_outlier_bwd_kernel(const float *__res
                                                               const int *__restrict__ idx,
                                                               const float *__restrict__ mask,
                                                               const float *__restrict__ g, const int *__restrict__ off,
-                                                              const int *__restrict__ list, int B, int K, int C, int k1,
-                                                              float *__restrict__ grad) {
+                                                              const int *__restrict__ list,
+                                                              const int *__restrict__ keys /*[B,K*k1] edge -> point or -1*/,
+                                                              int B, int K, int C, int k1, float *__restrict__ grad) {
   const long long total = (long long)B * K;
   for (long long gi = (long long)blockIdx.x * blockDim.x + threadIdx.x; gi < total;
        gi += (long long)gridDim.x * blockDim.x) {
@@ -329,13 +330,24 @@ __global__ void __launch_bounds__(256) knn_outlier_bwd_kernel(const float *__res
           a1 += 2.0f * (v1 - r[1]);
           a2 += 2.0f * (v2 - r[2]);
         }
-      int e = -1;
-      for (int q = p0; q < p1; ++q) {  // ascending edge order, whatever order the list was filled in
-        e = hg_csr_next(l, p0, p1, e);
-        const float *r = p + (size_t)(e / k1) * 3;
-        a0 += 2.0f * (v0 - r[0]);
-        a1 += 2.0f * (v1 - r[1]);
-        a2 += 2.0f * (v2 - r[2]);
+      if (p1 - p0 <= 32) {
+        int e = -1;
+        for (int q = p0; q < p1; ++q) {  // ascending edge order, whatever order the list was filled in
+          e = hg_csr_next(l, p0, p1, e);
+          const float *r = p + (size_t)(e / k1) * 3;
+          a0 += 2.0f * (v0 - r[0]);
+          a1 += 2.0f * (v1 - r[1]);
+          a2 += 2.0f * (v2 - r[2]);
+        }
+      } else {  // a hub (duplicated points): O(edges) scan of the forward map instead of the O(deg^2) selection walk
+        const int *kk = keys + (size_t)b * K * k1;
+        for (int e = 0; e < K * k1; ++e)
+          if (kk[e] == n) {
+            const float *r = p + (size_t)(e / k1) * 3;
+            a0 += 2.0f * (v0 - r[0]);
+            a1 += 2.0f * (v1 - r[1]);
+            a2 += 2.0f * (v2 - r[2]);
+          }
       }
       grad[(size_t)gi * 3] = coef * a0;
       grad[(size_t)gi * 3 + 1] = coef * a1;
@@ -347,10 +359,16 @@ __global__ void __launch_bounds__(256) knn_outlier_bwd_kernel(const float *__res
       float acc = 0.f;
       if (own)
         for (int t = 1; t < k1; ++t) acc += 2.0f * (v - p[(size_t)nb[t] * C + c]);
-      int e = -1;
-      for (int q = p0; q < p1; ++q) {  // ascending edge order, whatever order the list was filled in
-        e = hg_csr_next(l, p0, p1, e);
-        acc += 2.0f * (v - p[(size_t)(e / k1) * C + c]);
+      if (p1 - p0 <= 32) {
+        int e = -1;
+        for (int q = p0; q < p1; ++q) {  // ascending edge order, whatever order the list was filled in
+          e = hg_csr_next(l, p0, p1, e);
+          acc += 2.0f * (v - p[(size_t)(e / k1) * C + c]);
+        }
+      } else {
+        const int *kk = keys + (size_t)b * K * k1;
+        for (int e = 0; e < K * k1; ++e)
+          if (kk[e] == n) acc += 2.0f * (v - p[(size_t)(e / k1) * C + c]);
       }
       grad[(size_t)gi * C + c] = coef * acc;
     }
@@ -390,7 +408,8 @@ HG_API int hg_knn_self_temporal_f32(const float *pc, int B, int K, int C, int k1
   cudaStream_t stream = hg_stream(stream_);
   HG_REQUIRE(pc && idx, HG_E_BADARG, "knn_self: null pointer");
   HG_REQUIRE(B > 0 && K > 0 && C > 0, HG_E_BADARG, "knn_self: sizes must be positive");
-  HG_REQUIRE(k1 >= 1 && k1 <= 32 && k1 <= K, HG_E_BADARG, "knn_self: need 1 <= k <= min(32, K); got k=%d K=%d", k1, K);
+  HG_REQUIRE(k1 >= 1 && k1 <= (C == 3 ? 64 : 32) && k1 <= K, HG_E_BADARG,
+             "knn_self: need 1 <= k <= min(%d, K); got k=%d K=%d", C == 3 ? 64 : 32, k1, K);
   HG_REQUIRE(B <= 65535, HG_E_UNSUPPORTED, "knn_self: B=%d > 65535 clouds per call", B);
   if (C == 3)
     return hg_knn3_self_seeded_i32(pc, B, K, k1, vals, idx, workspace, workspace_bytes, stream, idx_state, state_valid);
@@ -425,7 +444,7 @@ HG_API int hg_knn_points_f32(const float *p1, const float *p2, int B, int N, int
                              hgStream stream_) {
   HG_REQUIRE(p1 && p2 && idx, HG_E_BADARG, "knn_points: null pointer");
   HG_REQUIRE(B > 0 && N > 0 && M > 0, HG_E_BADARG, "knn_points: sizes must be positive");
-  HG_REQUIRE(K >= 1 && K <= 32 && K <= M, HG_E_BADARG, "knn_points: need 1 <= K <= min(32, M); got K=%d M=%d", K, M);
+  HG_REQUIRE(K >= 1 && K <= 64 && K <= M, HG_E_BADARG, "knn_points: need 1 <= K <= min(64, M); got K=%d M=%d", K, M);
   HG_REQUIRE(B <= 65535, HG_E_UNSUPPORTED, "knn_points: B=%d > 65535 clouds per call", B);
   return hg_knn3_launch_i64(HG_KNN_FORM_DIRECT, p1, p2, B, N, M, K, dists, (long long *)idx, hg_stream(stream_));
 }
@@ -460,8 +479,8 @@ HG_API int hg_knn_outlier_bwd_f32(const float *pc, const int *idx, const float *
   HgCsr csr;
   int rc = hg_csr_build_unordered(keys, B, K * k1, K, csr_ws, hg_csr_workspace_bytes(B, K, K * k1), &csr, stream);
   if (rc) return rc;
-  knn_outlier_bwd_kernel<<<grid_for((long long)B * K, 256), 256, 0, stream>>>(pc, idx, mask, g, csr.off, csr.list, B, K,
-                                                                              C, k1, grad_pc);
+  knn_outlier_bwd_kernel<<<grid_for((long long)B * K, 256), 256, 0, stream>>>(pc, idx, mask, g, csr.off, csr.list, keys, B,
+                                                                              K, C, k1, grad_pc);
   HG_CHECK_LAUNCH("knn_outlier_bwd_kernel");
   return HG_OK;
 }

@@ -612,8 +612,8 @@ int launch_qt(const float *q, const float *r, int B, int Nq, int Nr, int k1, flo
 template <int FORM, typename IdxT>
 int launch_form(const float *q, const float *r, int B, int Nq, int Nr, int k1, float *vals, IdxT *idx,
                 const float *thr0, const float *sbound, cudaStream_t stream, int *idx_state = nullptr) {
-  if (k1 < 1 || k1 > 32) {
-    hg_set_error("knn: k=%d outside [1,32]", k1);
+  if (k1 < 1 || k1 > 64) {
+    hg_set_error("knn: k=%d outside [1,64]", k1);
     return HG_E_UNSUPPORTED;
   }
   // Queries per lane (QT): more queries amortise the candidate loads (LDS per pair halves with every doubling), which
@@ -632,7 +632,9 @@ int launch_form(const float *q, const float *r, int B, int Nq, int Nr, int k1, f
       return launch_qt<FORM, 2, 20, IdxT>(q, r, B, Nq, Nr, k1, vals, idx, thr0, sbound, stream, idx_state);
     if (k1 > 6 && k1 <= 20 && qt == 1)
       return launch_qt<FORM, 1, 20, IdxT>(q, r, B, Nq, Nr, k1, vals, idx, thr0, sbound, stream, idx_state);
-    if (k1 > 20 && qt == 1) return launch_qt<FORM, 1, 32, IdxT>(q, r, B, Nq, Nr, k1, vals, idx, thr0, sbound, stream, idx_state);
+    if (k1 > 20 && k1 <= 32 && qt == 1)
+      return launch_qt<FORM, 1, 32, IdxT>(q, r, B, Nq, Nr, k1, vals, idx, thr0, sbound, stream, idx_state);
+    if (k1 > 32 && qt == 1) return launch_qt<FORM, 1, 64, IdxT>(q, r, B, Nq, Nr, k1, vals, idx, thr0, sbound, stream, idx_state);
     hg_set_error("knn: forced QT=%d has no instantiation for k=%d", qt, k1);
     return HG_E_UNSUPPORTED;
   }
@@ -648,7 +650,9 @@ int launch_form(const float *q, const float *r, int B, int Nq, int Nr, int k1, f
       return launch_qt<FORM, 2, 20, IdxT>(q, r, B, Nq, Nr, k1, vals, idx, thr0, sbound, stream, idx_state);
     return launch_qt<FORM, 1, 20, IdxT>(q, r, B, Nq, Nr, k1, vals, idx, thr0, sbound, stream, idx_state);
   }
-  return launch_qt<FORM, 1, 32, IdxT>(q, r, B, Nq, Nr, k1, vals, idx, thr0, sbound, stream, idx_state);
+  if (k1 <= 32) return launch_qt<FORM, 1, 32, IdxT>(q, r, B, Nq, Nr, k1, vals, idx, thr0, sbound, stream, idx_state);
+  // 33..64 neighbours (HiT-ADV's default curv_loss_knn = 32 asks knn_points for 33): a 64-entry register list
+  return launch_qt<FORM, 1, 64, IdxT>(q, r, B, Nq, Nr, k1, vals, idx, thr0, sbound, stream, idx_state);
 }
 
 // ---- threshold seeding for self-kNN ---------------------------------------------------------------------------

@@ -30,6 +30,7 @@
 
 namespace {
 
+constexpr int kCsrWalkMax = 32;  // in-degree up to which the backward walks a reverse-map segment by selection
 constexpr int kColBatch = 32;  // rows per column-direction tracking batch (and rescan width of the finish kernel)
 
 struct NnParams {
@@ -389,7 +390,8 @@ __global__ void __launch_bounds__(256) set_loss_kernel(const float *__restrict__
 __global__ void __launch_bounds__(256) set_loss_bwd_kernel(
     const float *__restrict__ self_pts /*[B,Ns,D] points receiving the gradient*/,
     const float *__restrict__ other_pts /*[B,No,D]*/, const int *__restrict__ self_arg /*[B,Ns] -> other*/,
-    const int *__restrict__ rev_off /*[B,Ns+1]*/, const int *__restrict__ rev_list /*[B,No] other idx, ascending*/,
+    const int *__restrict__ rev_off /*[B,Ns+1]*/, const int *__restrict__ rev_list /*[B,No] other idx, any order*/,
+    const int *__restrict__ other_arg /*[B,No] -> self: the map rev_off/rev_list inverts*/,
     const float *__restrict__ g_self /*[B] upstream of the loss that gathers (self -> nearest other)*/,
     const float *__restrict__ g_other /*[B] upstream of the loss that scatters into self*/,
     const int *__restrict__ hd_self /*[B] or null*/, const int *__restrict__ hd_other /*[B] or null*/, int B, int Ns,
@@ -427,10 +429,18 @@ __global__ void __launch_bounds__(256) set_loss_bwd_kernel(
       float acc = 0.f;
       if (cs != 0.f) acc = cs * (2.0f * (v - po[(size_t)a * D + c]));
       float sc = 0.f;
-      int o = -1;
-      for (int q = p0; q < p1; ++q) {  // ascending source index, whatever order the list was filled in
-        o = hg_csr_next(lst, p0, p1, o);
-        if (mode == HG_MODE_CHAMFER || o == hdo) sc += 2.0f * (v - po[(size_t)o * D + c]);
+      if (p1 - p0 <= kCsrWalkMax) {
+        int o = -1;
+        for (int q = p0; q < p1; ++q) {  // ascending source index, whatever order the list was filled in
+          o = hg_csr_next(lst, p0, p1, o);
+          if (mode == HG_MODE_CHAMFER || o == hdo) sc += 2.0f * (v - po[(size_t)o * D + c]);
+        }
+      } else {
+        // a hub (collapsed / duplicated points: hundreds of sources share this nearest neighbour): the selection walk
+        // above is O(deg^2); scanning the forward map in ascending source order is O(No) and sums in the same order
+        const int *oa = other_arg + (size_t)b * No;
+        for (int o = 0; o < No; ++o)
+          if (oa[o] == s && (mode == HG_MODE_CHAMFER || o == hdo)) sc += 2.0f * (v - po[(size_t)o * D + c]);
       }
       grad_self[((size_t)b * Ns + s) * D + c] = acc + co * sc;
     }
@@ -597,8 +607,8 @@ HG_API int hg_set_loss_bwd_f32(const float *gts, const float *preds, const int *
     if (rc) return rc;
   }
   const long long tp = (long long)B * N1 * (D > 8 ? D : 1);
-  set_loss_bwd_kernel<<<grid_for(tp, 256), 256, 0, stream>>>(preds, gts, arg1, rev2.off, rev2.list, g1, g2, hd_arg1,
-                                                             hd_arg2, B, N1, N2, D, mode, grad_preds);
+  set_loss_bwd_kernel<<<grid_for(tp, 256), 256, 0, stream>>>(preds, gts, arg1, rev2.off, rev2.list, arg2, g1, g2,
+                                                             hd_arg1, hd_arg2, B, N1, N2, D, mode, grad_preds);
   HG_CHECK_LAUNCH("set_loss_bwd_kernel(preds)");
   if (grad_gts) {
     HgCsr rev1;
@@ -610,8 +620,8 @@ HG_API int hg_set_loss_bwd_f32(const float *gts, const float *preds, const int *
       if (rc) return rc;
     }
     const long long tg = (long long)B * N2 * (D > 8 ? D : 1);
-    set_loss_bwd_kernel<<<grid_for(tg, 256), 256, 0, stream>>>(gts, preds, arg2, rev1.off, rev1.list, g2, g1, hd_arg2,
-                                                               hd_arg1, B, N2, N1, D, mode, grad_gts);
+    set_loss_bwd_kernel<<<grid_for(tg, 256), 256, 0, stream>>>(gts, preds, arg2, rev1.off, rev1.list, arg1, g2, g1,
+                                                               hd_arg2, hd_arg1, B, N2, N1, D, mode, grad_gts);
     HG_CHECK_LAUNCH("set_loss_bwd_kernel(gts)");
   }
   return HG_OK;

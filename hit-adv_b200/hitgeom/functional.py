@@ -10,9 +10,29 @@ from ._lib import HitgeomError, check, lib, ptr, require, stream_ptr, workspace
 MODE_CHAMFER, MODE_HAUSDORFF = 0, 1
 
 
+def _on_tensor_device(fn):
+    """Run `fn` with the CUDA device of its first CUDA-tensor argument current (and the caller's restored): the C ABI
+    launches on `torch.cuda.current_stream()`, which belongs to the CURRENT device -- the reference's bindings have no
+    device guard either, here a tensor on another GPU must not launch on the wrong one."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kw):
+        for a in args:
+            if isinstance(a, torch.Tensor) and a.is_cuda:
+                if a.device.index != torch.cuda.current_device():
+                    with torch.cuda.device(a.device):
+                        return fn(*args, **kw)
+                break
+        return fn(*args, **kw)
+
+    return wrapper
+
+
 # ------------------------------------------------------------------------------------------------------------
 # set distance (util/set_distance.py)
 # ------------------------------------------------------------------------------------------------------------
+@_on_tensor_device
 def nn_bidir(gts, preds):
     """Fused `batch_pairwise_dist(gts, preds)` + `torch.min(P,1)` + `torch.min(P,2)` (set_distance.py:15-48).
 
@@ -35,6 +55,7 @@ def nn_bidir(gts, preds):
     return min1, arg1, min2, arg2
 
 
+@_on_tensor_device
 def pairwise_dist(x, y):
     require(x, "x", ndim=3)
     require(y, "y", ndim=3)
@@ -45,6 +66,7 @@ def pairwise_dist(x, y):
     return P
 
 
+@_on_tensor_device
 def set_loss(min1, min2, mode):
     B, N1 = min1.shape
     N2 = min2.shape[1]
@@ -58,6 +80,7 @@ def set_loss(min1, min2, mode):
     return loss1, loss2, hd1, hd2
 
 
+@_on_tensor_device
 def set_loss_bwd(gts, preds, arg1, arg2, hd1, hd2, g1, g2, mode, want_gts):
     B, N2, D = gts.shape
     N1 = preds.shape[1]
@@ -108,19 +131,24 @@ class SetDistanceFn(torch.autograd.Function):
     """(preds, gts) -> (loss1 [B], loss2 [B]) for Chamfer (mode 0) / Hausdorff (mode 1)."""
 
     @staticmethod
+    @_on_tensor_device
     def forward(ctx, preds, gts, mode):
         preds_c = preds.detach().contiguous()
         gts_c = gts.detach().contiguous()
         min1, arg1, min2, arg2 = shared_distance_pass.lookup(preds, gts, preds_c, gts_c)
         loss1, loss2, hd1, hd2 = set_loss(min1, min2, mode)
         ctx.mode = mode
-        ctx.saved = (preds_c, gts_c, arg1, arg2, hd1, hd2)
+        # save_for_backward (not a plain attribute): preds_c / gts_c alias the caller's storage when it is contiguous,
+        # and an in-place update between forward and backward must raise, as it does for the reference's autograd graph
+        ctx.save_for_backward(preds, gts, arg1, arg2, hd1, hd2)
         ctx.set_materialize_grads(False)  # an unused loss arrives as None, and its backward work is skipped
         return loss1, loss2
 
     @staticmethod
+    @_on_tensor_device
     def backward(ctx, g1, g2):
-        preds_c, gts_c, arg1, arg2, hd1, hd2 = ctx.saved
+        preds, gts, arg1, arg2, hd1, hd2 = ctx.saved_tensors
+        preds_c, gts_c = preds.detach().contiguous(), gts.detach().contiguous()
         B = preds_c.shape[0]
         dev = preds_c.device
         need_p, need_g = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
@@ -157,6 +185,7 @@ def hausdorff_losses(preds, gts):
 # ------------------------------------------------------------------------------------------------------------
 # kNN (util/dist_utils.py KNNDist, model/dgcnn_cls.py knn, pytorch3d.ops.knn_points)
 # ------------------------------------------------------------------------------------------------------------
+@_on_tensor_device
 def knn_self(pc, k1, want_vals=True, state=None, state_valid=False):
     """k1 smallest per row of dist[i,j] = (xx_j + (-2 zz_ij)) + xx_i.  pc [B,K,C] point-major.
 
@@ -182,6 +211,7 @@ class KnnOutlierFn(torch.autograd.Function):
     """pc [B,K,3] point-major -> per-sample kNN-outlier loss [B] (dist_utils.py:148-167, unit weights)."""
 
     @staticmethod
+    @_on_tensor_device
     def forward(ctx, pc, k, alpha, state=None, state_valid=False):
         pc_c = pc.detach().contiguous()
         B, K, C = pc_c.shape
@@ -192,13 +222,15 @@ class KnnOutlierFn(torch.autograd.Function):
         loss = torch.empty(B, dtype=torch.float32, device=dev)
         check(lib().hg_knn_outlier_fwd_f32(ptr(vals), B, K, k + 1, float(alpha), None, ptr(value), ptr(mask), ptr(loss),
                                            stream_ptr()), "hg_knn_outlier_fwd_f32")
-        ctx.saved = (pc_c, idx, mask)
+        ctx.save_for_backward(pc, idx, mask)
         ctx.k1 = k + 1
         return loss
 
     @staticmethod
+    @_on_tensor_device
     def backward(ctx, g):
-        pc_c, idx, mask = ctx.saved
+        pc, idx, mask = ctx.saved_tensors
+        pc_c = pc.detach().contiguous()
         B, K, C = pc_c.shape
         g = g.to(torch.float32).contiguous()
         grad = torch.empty_like(pc_c)
@@ -212,6 +244,7 @@ def knn_outlier_loss(pc, k, alpha, state=None, state_valid=False):
     return KnnOutlierFn.apply(_as_points(pc, "pc"), int(k), float(alpha), state, bool(state_valid))
 
 
+@_on_tensor_device
 def knn_points_raw(p1, p2, K):
     require(p1, "p1", ndim=3)
     require(p2, "p2", ndim=3)
@@ -226,6 +259,7 @@ def knn_points_raw(p1, p2, K):
 # ------------------------------------------------------------------------------------------------------------
 # torch-level seams of model/pointnet2_utils.py
 # ------------------------------------------------------------------------------------------------------------
+@_on_tensor_device
 def square_distance(src, dst):
     require(src, "src", ndim=3)
     require(dst, "dst", ndim=3)
@@ -236,6 +270,7 @@ def square_distance(src, dst):
     return out
 
 
+@_on_tensor_device
 def fps_torch(xyz, npoint, start):
     require(xyz, "xyz", ndim=3)
     require(start, "start", dtype=torch.int64, ndim=1)
@@ -245,6 +280,7 @@ def fps_torch(xyz, npoint, start):
     return out
 
 
+@_on_tensor_device
 def query_ball_torch(radius, nsample, xyz, new_xyz):
     require(xyz, "xyz", ndim=3)
     require(new_xyz, "new_xyz", ndim=3)
@@ -261,18 +297,26 @@ class IndexPointsFn(torch.autograd.Function):
     """points [B,N,C], idx [B,M] int64 -> [B,M,C]; backward is a deterministic segmented sum."""
 
     @staticmethod
+    @_on_tensor_device
     def forward(ctx, points, idx):
         pts = points.detach().contiguous()
+        require(pts, "points", ndim=3)
+        require(idx, "idx", dtype=torch.int64, ndim=2)
+        if idx.device != pts.device or idx.shape[0] != pts.shape[0]:
+            raise RuntimeError(f"index_points: idx {tuple(idx.shape)} on {idx.device} does not match points "
+                               f"{tuple(pts.shape)} on {pts.device}")
         B, N, C = pts.shape
         M = idx.shape[1]
         out = torch.empty((B, M, C), dtype=torch.float32, device=pts.device)
         check(lib().hg_index_points_f32(ptr(pts), ptr(idx), B, N, C, M, ptr(out), stream_ptr()), "hg_index_points_f32")
-        ctx.saved = (idx, N)
+        ctx.save_for_backward(idx)
+        ctx.n_points = N
         return out
 
     @staticmethod
+    @_on_tensor_device
     def backward(ctx, grad_out):
-        idx, N = ctx.saved
+        (idx,), N = ctx.saved_tensors, ctx.n_points
         g = grad_out.to(torch.float32).contiguous()
         B, M, C = g.shape
         grad = torch.empty((B, N, C), dtype=torch.float32, device=g.device)
@@ -287,6 +331,7 @@ class DeformFn(torch.autograd.Function):
     delta [B,J]) -> deformed cloud [B,3,K]; differentiable in perturb and delta."""
 
     @staticmethod
+    @_on_tensor_device
     def forward(ctx, ori, centers, perturb, delta):
         ori_c, cen_c = ori.detach().contiguous(), centers.detach().contiguous()
         per_c, del_c = perturb.detach().contiguous(), delta.detach().contiguous()
@@ -298,12 +343,15 @@ class DeformFn(torch.autograd.Function):
         deno = torch.empty((B, K), dtype=torch.float32, device=ori_c.device)
         check(lib().hg_hitadv_deform_fwd_f32(ptr(ori_c), ptr(cen_c), ptr(per_c), ptr(del_c), B, K, J, ptr(out), ptr(deno),
                                              stream_ptr()), "hg_hitadv_deform_fwd_f32")
-        ctx.saved = (ori_c, cen_c, per_c, del_c, out, deno)
+        ctx.save_for_backward(ori, centers, perturb, delta, out, deno)
         return out
 
     @staticmethod
+    @_on_tensor_device
     def backward(ctx, grad_out):
-        ori_c, cen_c, per_c, del_c, out, deno = ctx.saved
+        ori, centers, perturb, delta, out, deno = ctx.saved_tensors
+        ori_c, cen_c = ori.detach().contiguous(), centers.detach().contiguous()
+        per_c, del_c = perturb.detach().contiguous(), delta.detach().contiguous()
         B, _, K = ori_c.shape
         J = cen_c.shape[2]
         g = grad_out.to(torch.float32).contiguous()
@@ -322,6 +370,7 @@ class EdgeFeatureFn(torch.autograd.Function):
     """DGCNN edge features (dgcnn_cls.py:16-43): x [B,C,N], idx [B,N,k] int64 -> [B,2C,N,k] = cat(x_nbr - x, x)."""
 
     @staticmethod
+    @_on_tensor_device
     def forward(ctx, x, idx):
         xc = x.detach().contiguous()
         require(xc, "x")
@@ -332,12 +381,14 @@ class EdgeFeatureFn(torch.autograd.Function):
         k = ic.shape[2]
         out = torch.empty((B, 2 * C, N, k), dtype=torch.float32, device=xc.device)
         check(lib().hg_edge_feature_f32(ptr(xc), ptr(ic), B, C, N, k, ptr(out), stream_ptr()), "hg_edge_feature_f32")
-        ctx.saved = (ic, C)
+        ctx.save_for_backward(ic)
+        ctx.channels = C
         return out
 
     @staticmethod
+    @_on_tensor_device
     def backward(ctx, grad_out):
-        idx, C = ctx.saved
+        (idx,), C = ctx.saved_tensors, ctx.channels
         g = grad_out.to(torch.float32).contiguous()
         B, _, N, k = g.shape
         grad = torch.empty((B, C, N), dtype=torch.float32, device=g.device)

@@ -16,8 +16,33 @@ import torch
 from . import functional as F
 
 
+class _SquareDistanceFn(torch.autograd.Function):
+    """The reference's square_distance is plain torch (matmul + sums) and therefore differentiable:
+    PointNetFeaturePropagation differentiates its interpolation weights through it (model/pointnet2_utils.py:297-303).
+    Forward = the kernel (reference rounding order); backward = what autograd derives for d[n,m] = |s_n - t_m|^2:
+    grad_src[n] = 2 s_n sum_m g[n,m] - 2 (g @ dst)[n], grad_dst[m] = 2 t_m sum_n g[n,m] - 2 (g^T @ src)[m]."""
+
+    @staticmethod
+    def forward(ctx, src, dst):
+        ctx.save_for_backward(src, dst)
+        return F.square_distance(src.detach().contiguous(), dst.detach().contiguous())
+
+    @staticmethod
+    def backward(ctx, g):
+        src, dst = ctx.saved_tensors
+        gs = gd = None
+        if ctx.needs_input_grad[0]:
+            gs = 2.0 * (src * g.sum(dim=2, keepdim=True) - torch.bmm(g, dst))
+        if ctx.needs_input_grad[1]:
+            gd = 2.0 * (dst * g.sum(dim=1).unsqueeze(2) - torch.bmm(g.transpose(1, 2), src))
+        return gs, gd
+
+
 def square_distance(src, dst):
-    """[B,N,C] x [B,M,C] -> [B,N,M] = ((-2 src.dst) + |src|^2) + |dst|^2, the reference's rounding order."""
+    """[B,N,C] x [B,M,C] -> [B,N,M] = ((-2 src.dst) + |src|^2) + |dst|^2, the reference's rounding order;
+    differentiable in both arguments."""
+    if src.requires_grad or dst.requires_grad:
+        return _SquareDistanceFn.apply(src, dst)
     return F.square_distance(src.contiguous(), dst.contiguous())
 
 

@@ -28,6 +28,9 @@ def knn_gather(x, idx, lengths=None):
 def knn_points(p1, p2, lengths1=None, lengths2=None, norm=2, K=1, version=-1, return_nn=False, return_sorted=True):
     if lengths1 is not None or lengths2 is not None or norm != 2:
         raise NotImplementedError("knn_points: lengths / norm != 2 are not supported")
+    if int(K) > 64:
+        raise NotImplementedError(f"knn_points: K={K} > 64 neighbours is not supported by the streaming kernel "
+                                  "(register-resident lists; see INTEGRATION.md)")
     dists, idx = F.knn_points_raw(p1.detach().contiguous(), p2.detach().contiguous(), int(K))
     if p1.requires_grad or p2.requires_grad:
         # differentiable distances, recomputed from the gathered neighbours (pytorch3d's backward is the same

@@ -99,7 +99,7 @@ int hg_set_loss_bwd_f32(const float *gts, const float *preds, const int *arg1, c
  * util/dist_utils.py:148-156 (KNNDist) and model/dgcnn_cls.py:8-12 (DGCNN knn): the k1 smallest entries per
  * row of dist[i,j] = (xx_j + (-2*zz_ij)) + xx_i (DGCNN's pairwise_distance is exactly -dist).
  *   pc [B,K,C] point-major; vals [B,K,k1] ascending (may be NULL), idx [B,K,k1], lowest index first on ties.
- *   1 <= k1 <= 32, k1 <= K.
+ *   1 <= k1 <= 64 for C == 3 (32 otherwise), k1 <= K.
  * ------------------------------------------------------------------------------------------------------- */
 size_t hg_knn_self_workspace_bytes(int B, int K, int C, int k1);
 int hg_knn_self_f32(const float *pc, int B, int K, int C, int k1, float *vals, int *idx, void *workspace,
@@ -125,7 +125,8 @@ int hg_knn_outlier_bwd_f32(const float *pc, const int *idx, const float *mask, c
 
 /* pytorch3d.ops.knn_points(p1,p2,K) (requirements.txt:8; call sites ShapeAttack/HiT_ADV.py:78-80,320-321,
  * util/dist_utils.py:482-489, FGM/GeoA3_args.py:284): squared L2 from direct differences, K smallest
- * ascending, int64 indices.  p1 [B,N,3], p2 [B,M,3] -> dists [B,N,K], idx [B,N,K].  K <= 32. */
+ * ascending, int64 indices.  p1 [B,N,3], p2 [B,M,3] -> dists [B,N,K], idx [B,N,K].  K <= 64
+ * (HiT_ADV's default curv_loss_knn = 32 asks for 33). */
 int hg_knn_points_f32(const float *p1, const float *p2, int B, int N, int M, int K, float *dists, int64_t *idx,
                       hgStream stream);
 

@@ -157,3 +157,27 @@ def test_knn_generic_c_heavy_ties(oracle, F):
     vals, idx = F.knn_self(gpu(pc), 20)
     ov, oi = oracle.knn_self(pc, 20, threads=2)
     assert np.array_equal(vals.cpu().numpy(), ov) and np.array_equal(idx.cpu().numpy(), oi)
+
+
+def test_knn_outlier_backward_with_hub_points_vs_oracle(oracle):
+    """Padding by repetition: hundreds of points coincide, so a few points are the neighbour of hundreds of others
+    (in-degree far above the 32 the selection walk handles): the gradient is still the oracle's, promptly."""
+    import time
+
+    from hitgeom.dist_utils import KNNDist
+
+    pc = clouds(2, 2048, 31)
+    pc[0, 1000:1600] = pc[0, 5]
+    pc[1, 100:2000] = pc[1, 99] + 1e-4 * np.random.default_rng(0).standard_normal((1900, 3)).astype(np.float32)
+    a = gpu(pc).requires_grad_()
+    loss = KNNDist(k=5, alpha=0.2)(a, batch_avg=False)
+    torch.cuda.synchronize()
+    t0 = time.time()
+    loss.sum().backward()
+    torch.cuda.synchronize()
+    assert time.time() - t0 < 2.0
+    ol, (vals, idx, value, mask) = oracle.knn_dist(pc, 5, 0.2, threads=2)
+    assert mask.sum() > 0
+    np.testing.assert_allclose(loss.detach().cpu().numpy(), ol, rtol=1e-6, atol=1e-12)
+    # (sums of hundreds of terms: 1e-4, see test_backward_with_hub_points_vs_oracle)
+    assert normwise(a.grad.cpu().numpy(), oracle.knn_outlier_bwd(pc, idx, mask, np.ones(2, np.float32))) < 1e-4

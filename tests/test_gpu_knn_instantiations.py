@@ -163,3 +163,45 @@ def test_knndist_temporal_state_same_bits_as_stateless():
             y -= 0.5 * y.grad
         x.grad = None
         y.grad = None
+
+
+# ---- more than 32 neighbours (HiT_ADV's default curv_loss_knn = 32 asks knn_points for K = 33) -----------
+@pytest.mark.parametrize("K", [33, 50, 64])
+def test_knn_points_up_to_64_neighbours(oracle, F, K):
+    from hitgeom.pytorch3d_ops import knn_points
+
+    p1 = clouds(2, 300, 15, "surface")
+    p2 = clouds(2, 1500, 16, "surface")
+    p2[0, :60] = p2[0, 60:120]
+    od, oi = oracle.knn_points(p1, p2, K)
+    for gp in (2, 4):
+        F.force_knn_shape(1, gp)
+        out = knn_points(gpu(p1), gpu(p2), K=K)
+        assert np.array_equal(out.dists.cpu().numpy(), od) and np.array_equal(out.idx.cpu().numpy(), oi), (K, gp)
+    F.force_knn_shape(0, 0)
+    with pytest.raises(NotImplementedError):
+        knn_points(gpu(p1), gpu(p2), K=65)
+
+
+@pytest.mark.parametrize("n,k1", [(900, 40), (2500, 64)])
+def test_self_knn_up_to_64_neighbours(oracle, F, n, k1):
+    pc = _inputs(n)[0][1]
+    ov, oi = oracle.knn_self(pc, k1, threads=3)
+    vals, idx = F.knn_self(gpu(pc), k1)
+    assert np.array_equal(vals.cpu().numpy(), ov) and np.array_equal(idx.cpu().numpy(), oi)
+
+
+def test_default_constructed_hit_adv_runs():
+    """HiT_ADV(model, adv_func) with the reference's defaults (curv_loss_knn = 32 -> knn_points K = 33)."""
+    from hitgeom.hit_adv import HiT_ADV, UntargetedLogitsAdvLoss
+    from util_models import TinyPointNet
+
+    pts = clouds(3, 512, 8)
+    nrm = np.random.default_rng(2).standard_normal(pts.shape).astype(np.float32)
+    nrm /= np.linalg.norm(nrm, axis=-1, keepdims=True)
+    data = torch.from_numpy(np.concatenate([pts, nrm], -1))
+    att = HiT_ADV(TinyPointNet(40, seed=1), UntargetedLogitsAdvLoss(kappa=10.0), binary_step=1, num_iter=5,
+                  cd_weight=1e-4, ker_weight=1.0, hide_weight=1.0)
+    torch.manual_seed(0)
+    best, succ = att.attack(data, torch.zeros(3, dtype=torch.long))
+    assert best.shape == (3, 512, 3) and np.isfinite(best).all()

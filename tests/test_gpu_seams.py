@@ -68,3 +68,24 @@ def test_index_points_backward_is_deterministic_sum():
     pts.grad = None
     (ms.index_points(pts, idx) * w).sum().backward()
     assert torch.equal(g1, pts.grad)
+
+
+def test_square_distance_is_differentiable_like_the_reference():
+    """model/pointnet2_utils.py:19-40 is plain torch, so PointNetFeaturePropagation differentiates through it
+    (:297-303); the kernel-backed version must hand back the same gradients (torch's expression as the yardstick)."""
+    import torch
+
+    from hitgeom.model_seams import square_distance
+
+    g = torch.Generator().manual_seed(0)
+    src = torch.randn(2, 70, 3, generator=g).cuda().requires_grad_()
+    dst = torch.randn(2, 45, 3, generator=g).cuda().requires_grad_()
+    w = torch.randn(2, 70, 45, generator=g).cuda()
+    (square_distance(src, dst) * w).sum().backward()
+    s2, d2 = src.detach().double().requires_grad_(), dst.detach().double().requires_grad_()
+    ref = -2 * torch.matmul(s2, d2.permute(0, 2, 1)) + (s2 ** 2).sum(-1)[:, :, None] + (d2 ** 2).sum(-1)[:, None, :]
+    (ref * w.double()).sum().backward()
+    assert (src.grad.double() - s2.grad).abs().max() <= 1e-5 * s2.grad.abs().max()
+    assert (dst.grad.double() - d2.grad).abs().max() <= 1e-5 * d2.grad.abs().max()
+    only_dst = square_distance(src.detach(), dst)  # one-sided
+    assert only_dst.requires_grad

@@ -213,3 +213,37 @@ def test_shared_distance_pass_is_transparent():
         b = cd(adv, ori)
         assert a.item() != b.item()
     assert torch.equal(b.detach(), cd(adv, ori).detach())
+
+
+def test_backward_with_hub_points_vs_oracle(oracle):
+    """Degenerate clouds: thousands of sources sharing ONE nearest neighbour -- a collapsed adversarial
+    cloud, or padding by repetition.  The reverse-map walk switches from selection (O(deg^2)) to a forward-map scan for
+    in-degrees above 32; the gradient must still be the oracle's ascending-order sum and the call must return promptly."""
+    import time
+
+    from hitgeom import functional as F
+
+    B, N = 2, 4096
+    ori = clouds(B, N, 5)
+    adv = jitter(ori, 6)
+    adv[0, :] = adv[0, 0]          # cloud 0: the whole adversarial cloud collapsed onto one point
+    adv[1, : N // 2] = adv[1, 7]   # cloud 1: half of it
+    ori[1, N // 2:] = ori[1, 3]    # and half of the original cloud repeated
+    o, a = torch.from_numpy(ori).cuda(), torch.from_numpy(adv).cuda()
+    m1, a1, m2, a2 = F.nn_bidir(o, a)
+    for mode in (0, 1):
+        l1, l2, h1, h2 = F.set_loss(m1, m2, mode)
+        g1 = torch.tensor([0.7, 1.3], device="cuda")
+        g2 = torch.tensor([1.1, 0.4], device="cuda")
+        torch.cuda.synchronize()
+        t0 = time.time()
+        gp, gg = F.set_loss_bwd(o, a, a1, a2, h1, h2, g1, g2, mode, True)
+        torch.cuda.synchronize()
+        assert time.time() - t0 < 2.0
+        o1, oa1, o2, oa2 = oracle.nn_bidir(ori, adv)
+        assert np.array_equal(a1.cpu().numpy(), oa1) and np.array_equal(a2.cpu().numpy(), oa2)
+        _, _, oh1, oh2 = oracle.set_loss(o1, o2, mode)
+        wp, wg = oracle.set_loss_bwd(ori, adv, oa1, oa2, oh1, oh2, g1.cpu().numpy(), g2.cpu().numpy(), mode, want_gts=True)
+        # a hub's gradient is an FP32 sum of thousands of terms: FMA contraction alone (nvcc fuses 2*(v-x) into the
+        # accumulation, gcc does not) moves it by ~sqrt(deg) ulp, so the gate here is 1e-4, not the 1e-5 of regular clouds
+        assert normwise(gp.cpu().numpy(), wp) < 1e-4 and normwise(gg.cpu().numpy(), wg) < 1e-4, mode
