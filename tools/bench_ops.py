@@ -70,6 +70,46 @@ def main():
         print(r, flush=True)
 
     torch.manual_seed(0)
+    # ---- the distance losses against the reference's OWN torch path on the SAME GPU ("the real
+    # bar for C1/C4"): cuBLAS bmm + min / topk + autograd, util/set_distance.py:15-70, util/dist_utils.py:136-175 --------
+    from hitgeom.dist_utils import ChamferDist, ChamferkNNDist, HausdorffDist, KNNDist
+    from oracle import torch_port as tpl
+
+    torch.backends.cuda.matmul.allow_tf32 = False  # the reference (torch 1.11 defaults) multiplies in FP32
+    for (Bl, Nl) in ((388, 1024), (32, 1024)):
+        ori = torch.randn(Bl, Nl, 3, device="cuda")
+        ori = ori / ori.norm(dim=-1).amax(dim=1)[:, None, None]
+        adv = (ori + 0.01 * torch.randn_like(ori)).requires_grad_()
+        mods = {"ChamferDist": (ChamferDist(), lambda a, o: tpl.chamfer_dist(a, o), 1.0),
+                "HausdorffDist": (HausdorffDist(), lambda a, o: tpl.hausdorff_dist(a, o), 1.0),
+                "KNNDist(k=5)": (KNNDist(k=5), lambda a, o: tpl.knn_dist(a), 1.0),
+                "ChamferkNNDist": (ChamferkNNDist(), lambda a, o: tpl.chamfer_knn_dist(a, o), 2.0)}
+        for name, (mod, ref_fn, npass) in mods.items():
+            def fb_new():
+                adv.grad = None
+                (mod(adv) if name.startswith("KNN") else mod(adv, ori)).backward()
+
+            def fb_ref():
+                adv.grad = None
+                ref_fn(adv, ori).backward()
+
+            t_new, t_ref = timeit(fb_new, flush=flush), timeit(fb_ref, iters=5, flush=flush)
+            row(f"{name} fwd+bwd B={Bl} N={Nl}", t_new, t_ref,
+                extra={"pair_evals_per_s": npass * Bl * Nl * Nl / t_new * 1e3,
+                       "ref": "reference torch program (bmm + min/topk + autograd, FP32 matmul) on the same GPU"})
+
+        def c1_new():
+            adv.grad = None
+            with F.shared_distance_pass():
+                (mods["ChamferDist"][0](adv, ori) + mods["HausdorffDist"][0](adv, ori) + mods["KNNDist(k=5)"][0](adv)).backward()
+
+        def c1_ref():
+            adv.grad = None
+            (tpl.chamfer_dist(adv, ori) + tpl.hausdorff_dist(adv, ori) + tpl.knn_dist(adv)).backward()
+
+        row(f"config-1 step CD+HD+kNN fwd+bwd B={Bl} N={Nl} (eager launches)", timeit(c1_new, flush=flush),
+            timeit(c1_ref, iters=5, flush=flush),
+            extra={"ref": "reference torch program on the same GPU (it builds P twice + the kNN matrix)"})
     # ---- config 3 shapes: PointNet++ SSG, batch 64 x 1024 ----------------------------------------------------
     B, N = 64, 1024
     xyz = torch.randn(B, N, 3, device="cuda")
