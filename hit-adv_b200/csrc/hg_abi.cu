@@ -1,5 +1,6 @@
 // hg_abi.cu -- version, error reporting and device queries of the C ABI (include/hitgeom.h).
 #include <stdarg.h>
+#include <string.h>
 
 #include "hg_common.cuh"
 
@@ -14,7 +15,19 @@ void hg_set_error(const char *fmt, ...) {
 
 unsigned long long g_hg_launches = 0;
 
-HG_API int hg_version(void) { return 100; }
+HG_API int hg_version(void) { return 200; }
+
+// Development knobs (benchmarks / A-B experiments only; not part of the stable ABI): small integer switches by name.
+int g_hg_tune_scatter = 0;  // gather/group gradient: 0 auto, 1 single-buffer staged kernel, 2 bulk-copy pipeline
+HG_API int hg_tune(const char *key, int value) {
+  if (key == nullptr) return HG_E_BADARG;
+  if (!strcmp(key, "scatter")) {
+    g_hg_tune_scatter = value;
+    return HG_OK;
+  }
+  hg_set_error("hg_tune: unknown key '%s'", key);
+  return HG_E_BADARG;
+}
 
 HG_API unsigned long long hg_launch_count(void) { return g_hg_launches; }
 

@@ -24,6 +24,7 @@ void hg_set_error(const char *fmt, ...);
     }                                 \
   } while (0)
 
+extern int g_hg_tune_scatter;  // hg_tune("scatter", v): development knob, see hg_abi.cu
 extern unsigned long long g_hg_launches;  // kernels launched by this library (bench.py's gpu_launches)
 
 #define HG_CHECK_LAUNCH(name)                                            \
@@ -50,6 +51,18 @@ static inline cudaStream_t hg_stream(hgStream s) { return reinterpret_cast<cudaS
 static inline size_t hg_align(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
 int hg_sm_count();
+// true the first time it is called on the current device with this flag array (function attributes such as the
+// dynamic shared-memory limit are per device: one `static` flag per process would miss the second GPU)
+struct HgPerDeviceOnce {
+  unsigned char done[64] = {0};
+  bool first() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+    if (done[dev]) return false;
+    done[dev] = 1;
+    return true;
+  }
+};
 
 // per-kernel device timing hooks (hg_abi.cu); tags are part of the ABI (include/hitgeom.h HG_PROF_*)
 bool hg_prof_begin(int tag, cudaStream_t s);
@@ -97,6 +110,53 @@ __device__ __forceinline__ float hg_warp_max_f32(float v) {
   float m;
   asm("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(m) : "f"(v));
   return m;
+}
+
+// ---- bulk asynchronous copies (TMA unit, 1-D): global -> shared, completion on an mbarrier ------------------------
+// cp.async.bulk (SASS: UBLKCP) moves a whole contiguous block with ONE instruction issued by one thread; the copy
+// engine keeps it in flight while the CTA computes on the previous block.  Sizes and both addresses must be multiples
+// of 16 bytes.  hg_mbar_wait spins on the phase parity (try_wait suspends the thread in hardware between polls).
+__device__ __forceinline__ unsigned hg_smem_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void hg_mbar_init(uint64_t *bar, unsigned arrivals) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(hg_smem_addr(bar)), "r"(arrivals) : "memory");
+}
+__device__ __forceinline__ void hg_mbar_init_fence() {  // make the initialised barriers visible to the async proxy
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void hg_mbar_expect_tx(uint64_t *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(hg_smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void hg_bulk_g2s(void *dst_smem, const void *src_gmem, unsigned bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   hg_smem_addr(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(hg_smem_addr(bar))
+               : "memory");
+}
+__device__ __forceinline__ void hg_mbar_wait(uint64_t *bar, unsigned parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "HG_WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra HG_DONE_%=;\n\t"
+      "bra HG_WAIT_%=;\n\t"
+      "HG_DONE_%=:\n\t"
+      "}" ::"r"(hg_smem_addr(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+// __match_any_sync on keys of `nbits` bits, built from ballots: MATCH.ANY resolves one distinct value at a time (about
+// 600 cycles for 32 distinct keys, measured through the CSR builder: 48 us for 16k edges per cloud), a ballot per key
+// bit costs a few cycles each
+__device__ __forceinline__ unsigned hg_match_any_bits(int key, int nbits) {
+  unsigned same = 0xffffffffu;
+  for (int b = 0; b < nbits; ++b) {
+    const bool bit = (key >> b) & 1;
+    const unsigned v = __ballot_sync(0xffffffffu, bit);
+    same &= bit ? v : ~v;
+  }
+  return same;
 }
 
 // ---- deterministic reverse map (CSR) used by every scatter-style backward ----------------------------------

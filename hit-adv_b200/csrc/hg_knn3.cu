@@ -944,25 +944,19 @@ int knn3_small_self(const float *pc, int B, int N, int k1, float *vals, int *idx
   const size_t seed_smem = (size_t)N * (sizeof(float4) + 2 * sizeof(int));
   // window of the Z-order scan: enough points for a k1-th smallest that is close to the true one
   const int win = k1 <= 8 ? 32 : (k1 <= 16 ? 48 : 64);
-  static bool attr_set[3] = {false, false, false};
+  static HgPerDeviceOnce once[3];
   constexpr int kSeedMaxSmem = 8192 * (int)(sizeof(float4) + 2 * sizeof(int));
   if (k1 <= 6) {
-    if (!attr_set[0]) {
+    if (once[0].first())
       HG_CUDA(cudaFuncSetAttribute(knn_seed_small_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSeedMaxSmem));
-      attr_set[0] = true;
-    }
     knn_seed_small_kernel<6><<<B, 256, seed_smem, stream>>>(pc, N, k1, win, thr0, sbound);
   } else if (k1 <= 20) {
-    if (!attr_set[1]) {
+    if (once[1].first())
       HG_CUDA(cudaFuncSetAttribute(knn_seed_small_kernel<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSeedMaxSmem));
-      attr_set[1] = true;
-    }
     knn_seed_small_kernel<20><<<B, 256, seed_smem, stream>>>(pc, N, k1, win, thr0, sbound);
   } else {
-    if (!attr_set[2]) {
+    if (once[2].first())
       HG_CUDA(cudaFuncSetAttribute(knn_seed_small_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSeedMaxSmem));
-      attr_set[2] = true;
-    }
     knn_seed_small_kernel<32><<<B, 256, seed_smem, stream>>>(pc, N, k1, win, thr0, sbound);
   }
   HG_CHECK_LAUNCH("knn_seed_small_kernel");

@@ -198,15 +198,169 @@ __global__ void __launch_bounds__(kScatterThreads) scatter_staged_kernel(const f
   }
 }
 
-// gradient of gather / group: staged kernel when the plane fits in shared memory, generic kernel otherwise
+// The same sums with the planes streamed by the copy engine: a CTA owns a contiguous run of (b,c) planes (the reverse
+// map of a cloud stays in L1 across its channels) and double-buffers them in shared memory -- while the 256 threads sum
+// plane i out of one buffer, ONE cp.async.bulk (UBLKCP) brings the whole of plane i+1 into the other, completion on an
+// mbarrier.  The staged kernel above loads, barriers, computes, barriers: its loads never overlap its sums.
+constexpr int kBulkThreads = 1024, kBulkWarps = kBulkThreads / 32;
+// LIST_SMEM: the reverse map of the current cloud (shared by its c planes) also lives in shared memory, re-laid-out so
+// that a warp reads it without bank conflicts: the lists of 32 consecutive keys are interleaved ("sliced ELL":
+// entry j of key 32*blk + lane sits at base[blk] + 32*j + lane, each block padded to its longest list), 16 bits per
+// entry.  Read from global memory every batch of entries is an L2 round trip in the middle of a dependent chain; kept
+// in CSR order in shared memory, lanes whose lists start ~deg entries apart collide on a handful of banks (ncu: 57 %
+// of the kernel's shared-memory wavefronts were conflict replays).  A cloud whose padded lists do not fit (hub keys)
+// falls back to the global-memory walk for that cloud.
+template <bool LIST_SMEM>
+__global__ void __launch_bounds__(kBulkThreads) scatter_bulk_kernel(const float *__restrict__ src,
+                                                                    const int *__restrict__ off,
+                                                                    const int *__restrict__ list, int c, int n, int E,
+                                                                    long long planes, float *__restrict__ grad_points,
+                                                                    int sc_total, int sc_off, int cap /*ELL entries*/) {
+  extern __shared__ __align__(128) float sB[];  // [2][E] planes, then (LIST_SMEM) so [n+1], sbase [nblk+1], ELL [cap]
+  const int nblk = (n + 31) / 32;
+  int *so = reinterpret_cast<int *>(sB + 2 * (size_t)E);
+  int *sbase = so + (n + 1);
+  unsigned short *sl = reinterpret_cast<unsigned short *>(sbase + (nblk + 1));
+  __shared__ __align__(8) uint64_t bar[2];
+  __shared__ int ell_ok;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long per = (planes + gridDim.x - 1) / gridDim.x;
+  const long long p_lo = (long long)blockIdx.x * per, p_hi = min(planes, p_lo + per);
+  if (p_lo >= p_hi) return;
+  const unsigned bytes = (unsigned)E * sizeof(float);
+  auto plane_src = [&](long long bc) { return src + ((size_t)(bc / c) * sc_total + sc_off + (int)(bc % c)) * E; };
+  if (threadIdx.x == 0) {
+    hg_mbar_init(&bar[0], 1);
+    hg_mbar_init(&bar[1], 1);
+    hg_mbar_init_fence();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    hg_mbar_expect_tx(&bar[0], bytes);
+    hg_bulk_g2s(sB, plane_src(p_lo), bytes, &bar[0]);
+  }
+  int it = 0;
+  long long cloud = -1;
+  for (long long bc = p_lo; bc < p_hi; ++bc, ++it) {
+    const int cur = it & 1;
+    if (threadIdx.x == 0 && bc + 1 < p_hi) {  // the other buffer was released by the barrier that ended iteration it-1
+      hg_mbar_expect_tx(&bar[cur ^ 1], bytes);
+      hg_bulk_g2s(sB + (size_t)(cur ^ 1) * E, plane_src(bc + 1), bytes, &bar[cur ^ 1]);
+    }
+    const long long bi = bc / c;
+    const int *o = off + (size_t)bi * (n + 1);
+    const int *l = list + (size_t)bi * E;
+    if (LIST_SMEM && bi != cloud) {  // new cloud: build its interleaved map
+      cloud = bi;
+      for (int i = threadIdx.x; i <= n; i += kBulkThreads) so[i] = o[i];
+      __syncthreads();
+      for (int blk = warp; blk < nblk; blk += kBulkWarps) {  // longest list of every block of 32 keys
+        const int key = blk * 32 + lane;
+        const int deg = key < n ? so[key + 1] - so[key] : 0;
+        const int m = __reduce_max_sync(0xffffffffu, deg);
+        if (lane == 0) sbase[blk + 1] = 32 * m;
+      }
+      __syncthreads();
+      if (warp == 0) {  // exclusive prefix over the blocks
+        int run = 0;
+        for (int b0 = 0; b0 < nblk; b0 += 32) {
+          const int i = b0 + lane;
+          const int v = i < nblk ? sbase[i + 1] : 0;
+          int incl = v;
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+          }
+          if (i < nblk) sbase[i + 1] = run + incl;
+          run += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (lane == 0) {
+          sbase[0] = 0;
+          ell_ok = run <= cap;
+        }
+      }
+      __syncthreads();
+      if (ell_ok) {
+        for (int blk = warp; blk < nblk; blk += kBulkWarps) {
+          const int key = blk * 32 + lane;
+          const int q0 = key < n ? so[key] : 0, deg = key < n ? so[key + 1] - q0 : 0;
+          unsigned short *dst = sl + sbase[blk] + lane;
+          for (int j = 0; j < deg; ++j) dst[32 * j] = (unsigned short)__ldg(l + q0 + j);
+        }
+      }
+      __syncthreads();
+    }
+    hg_mbar_wait(&bar[cur], (unsigned)(it >> 1) & 1u);
+    const float *sA = sB + (size_t)cur * E;
+    float *dst = grad_points + (size_t)bc * n;
+    if (LIST_SMEM && ell_ok) {
+      for (int blk = warp; blk < nblk; blk += kBulkWarps) {
+        const int key = blk * 32 + lane;
+        const int deg = key < n ? so[key + 1] - so[key] : 0;
+        const unsigned short *lp = sl + sbase[blk] + lane;
+        float acc = 0.f;
+        int j = 0;
+        for (; j + 3 < deg; j += 4) {  // four entries in flight; the sum itself stays sequential (ascending edge)
+          const int e0 = lp[32 * j], e1 = lp[32 * j + 32], e2 = lp[32 * j + 64], e3 = lp[32 * j + 96];
+          const float v0 = sA[e0], v1 = sA[e1], v2 = sA[e2], v3 = sA[e3];
+          acc = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(acc, v0), v1), v2), v3);
+        }
+        for (; j < deg; ++j) acc = __fadd_rn(acc, sA[lp[32 * j]]);
+        if (key < n) dst[key] = acc;
+      }
+    } else {
+      for (int key = threadIdx.x; key < n; key += kBulkThreads) {
+        const int q1 = o[key + 1];
+        int q = o[key];
+        float acc = 0.f;
+        for (; q + 3 < q1; q += 4) {
+          const int e0 = __ldg(l + q), e1 = __ldg(l + q + 1), e2 = __ldg(l + q + 2), e3 = __ldg(l + q + 3);
+          const float v0 = sA[e0], v1 = sA[e1], v2 = sA[e2], v3 = sA[e3];
+          acc = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(acc, v0), v1), v2), v3);
+        }
+        for (; q < q1; ++q) acc = __fadd_rn(acc, sA[__ldg(l + q)]);
+        dst[key] = acc;
+      }
+    }
+    __syncthreads();  // every thread is done with this buffer (and this cloud's map) before the copy engine refills it
+  }
+}
+
+// gradient of gather / group: bulk-copy pipeline when two planes fit in shared memory (and the planes are 16-byte
+// aligned), single-buffer staged kernel when one does, generic kernel otherwise
 int launch_scatter_unweighted(const float *grad_out, const HgCsr &csr, int b, int c, int n, int E, float *grad_points,
                               cudaStream_t stream, int sc_total = 0, int sc_off = 0) {
   if (sc_total == 0) sc_total = c;
   const size_t smem = (size_t)E * sizeof(float);
-  if (smem <= 100 * 1024 && E >= n) {  // (two CTAs per SM)
+  const long long planes = (long long)b * c;
+  const bool bulk_ok = 2 * smem <= 200 * 1024 && E >= n && (E & 3) == 0 && (reinterpret_cast<uintptr_t>(grad_out) & 15) == 0;
+  if (bulk_ok && g_hg_tune_scatter != 1 && (planes >= 2LL * hg_sm_count() || g_hg_tune_scatter >= 2)) {
+    static HgPerDeviceOnce once;
+    if (once.first()) {
+      HG_CUDA(cudaFuncSetAttribute(scatter_bulk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+      HG_CUDA(cudaFuncSetAttribute(scatter_bulk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    }
+    // shared memory beyond the two plane buffers goes to the cloud's interleaved map: it needs ~1.6 E entries for
+    // Poisson-like in-degrees (longest of 32 lists); take what is there, the kernel falls back per cloud if it overflows
+    const size_t fixed = 2 * smem + ((size_t)(n + 1) + (size_t)((n + 31) / 32 + 1)) * sizeof(int);
+    const size_t limit = 220 * 1024;
+    long long cap = fixed < limit ? (long long)((limit - fixed) / sizeof(unsigned short)) : 0;
+    if (cap > 4LL * E) cap = 4LL * E;
+    const bool list_smem = cap >= (long long)E + 32LL * ((n + 31) / 32) && E <= 65535 && g_hg_tune_scatter != 3;
+    const size_t dyn = list_smem ? fixed + (size_t)cap * sizeof(unsigned short) : 2 * smem;
+    const int per_sm = (dyn <= 100 * 1024) ? 2 : 1;
+    long long grid = (long long)hg_sm_count() * per_sm;
+    if (grid > planes) grid = planes;
+    if (list_smem)
+      scatter_bulk_kernel<true><<<(int)grid, kBulkThreads, dyn, stream>>>(grad_out, csr.off, csr.list, c, n, E, planes,
+                                                                         grad_points, sc_total, sc_off, (int)cap);
+    else
+      scatter_bulk_kernel<false><<<(int)grid, kBulkThreads, dyn, stream>>>(grad_out, csr.off, csr.list, c, n, E, planes,
+                                                                          grad_points, sc_total, sc_off, 0);
+  } else if (smem <= 100 * 1024 && E >= n) {  // (two CTAs per SM)
     if (smem > 48 * 1024)
       HG_CUDA(cudaFuncSetAttribute(scatter_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const long long planes = (long long)b * c;
     long long grid = planes;
     const long long cap = (long long)hg_sm_count() * 8;
     if (grid > cap) grid = cap;

@@ -27,6 +27,7 @@ _SIGNATURES = {
     "hg_knn_tune": (None, [I, I]),
     "hg_knn_force_shape": (None, [I, I]),
     "hg_knn_tune_small": (None, [I]),
+    "hg_tune": (I, [ctypes.c_char_p, I]),
     "hg_launch_count": (ctypes.c_ulonglong, []),
     "hg_prof_enable": (None, [I]),
     "hg_prof_read": (I, [I, ctypes.POINTER(F), ctypes.POINTER(I)]),

@@ -49,6 +49,8 @@ int hg_device_info(int *sm_count, int *clock_khz, long long *l2_bytes, long long
 #define HG_PROF_FPS 2      /* fps_kernel */
 #define HG_PROF_GROUP 3    /* gather_channel_major_kernel (group_points / gather_points) */
 #define HG_PROF_NTAGS 4
+/* Development knobs for A/B measurements (not part of the stable ABI): "scatter" = 0 auto / 1 staged / 2 bulk-copy. */
+int hg_tune(const char *key, int value);
 unsigned long long hg_launch_count(void); /* kernels launched by this library since it was loaded */
 void hg_prof_enable(int on);
 int hg_prof_read(int tag, float *total_ms, int *launches);

@@ -10,7 +10,24 @@ SUBSET_RACE="tests/test_gpu_knn.py::test_knn_topk_golden tests/test_gpu_knn.py::
 timeout 1500 compute-sanitizer --tool memcheck --error-exitcode 9 --launch-timeout 0 \
   python -m pytest $SUBSET_MEM -x -q -p no:cacheprovider > gpurun_out/sanitizer_memcheck.log 2>&1
 echo "memcheck exit code: $?" >> gpurun_out/sanitizer_memcheck.log
-timeout 1500 compute-sanitizer --tool racecheck --racecheck-report all --error-exitcode 9 \
+timeout 1500 compute-sanitizer --tool racecheck --racecheck-report all --print-limit 0 --error-exitcode 9 \
   python -m pytest $SUBSET_RACE -x -q -p no:cacheprovider > gpurun_out/sanitizer_racecheck.log 2>&1
 echo "racecheck exit code: $?" >> gpurun_out/sanitizer_racecheck.log
-tail -5 gpurun_out/sanitizer_memcheck.log gpurun_out/sanitizer_racecheck.log
+# hazards by library: tests/test_gpu_pointnet2.py also runs the REFERENCE's kernels (oracle/_ref/_ext_ref.so) for comparison
+python - <<'PY' >> gpurun_out/sanitizer_racecheck.log
+import re
+txt = open("gpurun_out/sanitizer_racecheck.log", errors="replace").read()
+blocks = re.split(r"\n(?==========+ (?:Error|Warning))", txt)
+by = {}
+for b in blocks:
+    if not re.match(r"=+ (Error|Warning)", b):
+        continue
+    lib = "libhitgeom.so" if "libhitgeom" in b else "_ext_ref.so (reference kernels)" if "_ext_ref" in b else "other"
+    m = re.search(r"at (?:void )?([^+(<]+)", b)
+    by[(lib, m.group(1).strip() if m else "?")] = by.get((lib, m.group(1).strip() if m else "?"), 0) + 1
+print("hazard reports by library / kernel:")
+for k, v in sorted(by.items(), key=lambda kv: -kv[1]):
+    print(f"  {v:6d}  {k[0]}  {k[1]}")
+print("hitgeom hazards:", sum(v for k, v in by.items() if k[0] == "libhitgeom.so"))
+PY
+tail -5 gpurun_out/sanitizer_memcheck.log; tail -12 gpurun_out/sanitizer_racecheck.log
