@@ -25,6 +25,10 @@ HG_API int hg_tune(const char *key, int value) {
     g_hg_tune_scatter = value;
     return HG_OK;
   }
+  if (!strcmp(key, "nn_exact")) {
+    g_hg_tune_nn_exact = value;
+    return HG_OK;
+  }
   hg_set_error("hg_tune: unknown key '%s'", key);
   return HG_E_BADARG;
 }

@@ -21,6 +21,18 @@ def F():
     return functional
 
 
+@pytest.fixture(autouse=True, params=["approx-tracker", "exact-tracker"])
+def _tracker(request):
+    """Every test of this module runs twice: with the default distance pass (5-operation exact tracker) and with the
+    experimental 4-operation approximate tracker + exact recovery in the finish kernels (hg_tune("nn_exact", 0),
+    hg_nn_bidir.cu).  Both must give the reference's bits."""
+    from hitgeom._lib import lib
+
+    lib().hg_tune(b"nn_exact", 1 if request.param == "exact-tracker" else 0)
+    yield request.param
+    lib().hg_tune(b"nn_exact", 1)
+
+
 @pytest.mark.parametrize("name", ["setdist_eq", "setdist_ragged", "setdist_dups"])
 @pytest.mark.parametrize("T", [0, 8, 16])
 def test_nn_bidir_golden(golden, F, name, T):
@@ -247,3 +259,53 @@ def test_backward_with_hub_points_vs_oracle(oracle):
         # a hub's gradient is an FP32 sum of thousands of terms: FMA contraction alone (nvcc fuses 2*(v-x) into the
         # accumulation, gcc does not) moves it by ~sqrt(deg) ulp, so the gate here is 1e-4, not the 1e-5 of regular clouds
         assert normwise(gp.cpu().numpy(), wp) < 1e-4 and normwise(gg.cpu().numpy(), wg) < 1e-4, mode
+
+
+@pytest.mark.parametrize("case", ["dups across batches", "far from origin", "all equal", "lattice", "tiny spacings"])
+def test_nn_bidir_ambiguous_inputs_vs_oracle(oracle, F, case):
+    """Inputs built to defeat the approximate tracker: exact duplicates spread over different 32-row batches and
+    different lanes (runner-up == winner), clouds far from the origin (the error bound eps2 ~ 1e-6 * |p|^2 exceeds the
+    nearest-neighbour gaps: everything is ambiguous), a cloud of identical points, an integer lattice (massive exact
+    ties), and spacings of a few ulp.  Values and first indices must be the oracle's, bit for bit."""
+    rng = np.random.default_rng(len(case))
+    B, N = 2, 1500
+    gts = clouds(B, N, 17, "gauss")
+    preds = jitter(gts, 3)
+    if case == "dups across batches":
+        src = rng.integers(0, N, 400)
+        dst = rng.integers(0, N, 400)
+        gts[0, dst] = gts[0, src]
+        preds[1, dst] = preds[1, src]
+        preds[0, :200] = gts[0, :200]  # exact coincidences between the clouds too
+    elif case == "far from origin":
+        gts = (gts * 0.05 + np.asarray((300.0, -200.0, 150.0), np.float32)).astype(np.float32)
+        preds = (preds * 0.05 + np.asarray((300.0, -200.0, 150.0), np.float32)).astype(np.float32)
+    elif case == "all equal":
+        gts[:] = gts[:, :1]
+        preds[:] = gts[:, :1]
+        preds[1, 700] += 1e-3
+    elif case == "lattice":
+        gts = rng.integers(-3, 4, size=(B, N, 3)).astype(np.float32)
+        preds = rng.integers(-3, 4, size=(B, N, 3)).astype(np.float32)
+    else:
+        preds = (gts + rng.integers(-2, 3, size=gts.shape) * np.spacing(np.abs(gts))).astype(np.float32)
+    for T, RB in ((0, 0), (16, 64), (8, 32)):
+        F.tune_nn_bidir(T, RB)
+        try:
+            m1, a1, m2, a2 = F.nn_bidir(gpu(gts), gpu(preds))
+        finally:
+            F.tune_nn_bidir(0, 0)
+        o1, oa1, o2, oa2 = oracle.nn_bidir(gts, preds, threads=2)
+        assert np.array_equal(a1.cpu().numpy(), oa1) and np.array_equal(a2.cpu().numpy(), oa2), (case, T, RB)
+        assert np.array_equal(m1.cpu().numpy(), o1) and np.array_equal(m2.cpu().numpy(), o2), (case, T, RB)
+
+
+def test_nn_bidir_large_cloud_vs_oracle(oracle, F):
+    """One configuration-5-sized cloud pair (16384 points, T = 16, RB = 512, four warps per CTA)."""
+    gts = clouds(2, 16384, 5)
+    preds = jitter(gts, 6)
+    preds[1, :3000] = gts[1, 5000:8000]
+    m1, a1, m2, a2 = F.nn_bidir(gpu(gts), gpu(preds))
+    o1, oa1, o2, oa2 = oracle.nn_bidir(gts, preds, threads=2)
+    assert np.array_equal(a1.cpu().numpy(), oa1) and np.array_equal(a2.cpu().numpy(), oa2)
+    assert np.array_equal(m1.cpu().numpy(), o1) and np.array_equal(m2.cpu().numpy(), o2)
