@@ -24,6 +24,7 @@ void hg_set_error(const char *fmt, ...);
     }                                 \
   } while (0)
 
+extern int g_hg_tune_knn_tc_off;  // hg_tune("knn_tc", 1) switches the tensor-core kNN prefilter off
 extern int g_hg_tune_nn_exact;  // hg_tune("nn_exact", v), see hg_nn_bidir.cu
 extern int g_hg_tune_scatter;  // hg_tune("scatter", v): development knob, see hg_abi.cu
 extern unsigned long long g_hg_launches;  // kernels launched by this library (bench.py's gpu_launches)
@@ -184,6 +185,11 @@ __device__ __forceinline__ int hg_csr_next(const int *__restrict__ list, int p0,
   }
   return best;
 }
+
+// ---- tensor-core kNN prefilter for feature clouds (hg_knn_tc.cu) ---------------------------------------------------
+bool hg_knn_tc_supported(int K, int C, int k1);
+int hg_knn_tc_run(const float *pc, const float *xx, int B, int K, int C, int k1, float *vals, int *idx, void *scratch,
+                  size_t scratch_bytes, cudaStream_t stream);
 
 // ---- 3-D streaming kNN (hg_knn3.cu) ---------------------------------------------------------------------------
 #define HG_KNN_FORM_EXPANDED 0  // dist = (xx_j + (-2 zz)) + xx_i   (KNNDist / DGCNN)

@@ -50,6 +50,7 @@ int hg_device_info(int *sm_count, int *clock_khz, long long *l2_bytes, long long
 #define HG_PROF_GROUP 3    /* gather_channel_major_kernel (group_points / gather_points) */
 #define HG_PROF_NTAGS 4
 /* Development knobs for A/B measurements (not part of the stable ABI): "scatter" = 0 auto / 1 staged / 2 bulk-copy;
+ * "knn_tc" = 1 switches the tensor-core kNN prefilter of feature clouds off, 2 forces it for small batches;
  * "nn_exact" = 0 runs the experimental 4-operation approximate tracker (+ exact recovery) in hg_nn_bidir_f32
  * instead of the default 5-operation exact tracker (same results; see hg_nn_bidir.cu for why it is not the default). */
 int hg_tune(const char *key, int value);

@@ -181,3 +181,38 @@ def test_knn_outlier_backward_with_hub_points_vs_oracle(oracle):
     np.testing.assert_allclose(loss.detach().cpu().numpy(), ol, rtol=1e-6, atol=1e-12)
     # (sums of hundreds of terms: 1e-4, see test_backward_with_hub_points_vs_oracle)
     assert normwise(a.grad.cpu().numpy(), oracle.knn_outlier_bwd(pc, idx, mask, np.ones(2, np.float32))) < 1e-4
+
+
+# ---- tensor-core prefilter (hg_knn_tc.cu): same values and indices as the FP32 path and the oracle --------------------
+@pytest.mark.parametrize("tc_off", [2, 1])
+@pytest.mark.parametrize("C,K,k1,kind", [(64, 1024, 20, "gauss"), (128, 512, 20, "gauss"), (32, 300, 7, "gauss"),
+                                         (96, 777, 32, "gauss"), (64, 512, 20, "prototypes"), (64, 640, 5, "scaled"),
+                                         (128, 1024, 20, "dups")])
+def test_knn_feature_clouds_tensor_core_vs_oracle(oracle, F, C, K, k1, kind, tc_off):
+    """DGCNN-shaped feature clouds (C a multiple of 32, 256 <= K <= 4096) take the tcgen05 TF32 prefilter + exact FP32
+    re-evaluation (`hg_tune("knn_tc", 2)` forces it for batches too small to fill the machine, as here);
+    `hg_tune("knn_tc", 1)` forces the FP32 tile + row-select path.  Both must give the oracle's values
+    and indices bit for bit -- including feature clouds made of a few prototypes (massive exact ties: the candidate
+    lists overflow and the rows are re-evaluated in full), widely different feature scales (the TF32 error bound is
+    per row) and duplicated points."""
+    from hitgeom._lib import lib
+
+    rng = np.random.default_rng(C + K)
+    pc = rng.standard_normal((2, K, C)).astype(np.float32)
+    if kind == "prototypes":
+        protos = rng.standard_normal((5, C)).astype(np.float32)
+        pc = protos[rng.integers(0, 5, size=(2, K))]
+        pc[1, : K // 2] = protos[0]
+    elif kind == "scaled":
+        pc *= np.exp(rng.uniform(-4, 4, size=(2, K, 1))).astype(np.float32)
+    elif kind == "dups":
+        pc[0, 100:400] = pc[0, 500:800]
+        pc[1, :] = pc[1, rng.integers(0, 64, size=K)]
+    lib().hg_tune(b"knn_tc", tc_off)
+    try:
+        vals, idx = F.knn_self(gpu(pc), k1)
+    finally:
+        lib().hg_tune(b"knn_tc", 0)
+    ov, oi = oracle.knn_self(pc, k1, threads=2)
+    assert np.array_equal(idx.cpu().numpy(), oi), (kind, "indices")
+    assert np.array_equal(vals.cpu().numpy(), ov), (kind, "values")
