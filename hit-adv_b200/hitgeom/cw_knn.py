@@ -84,6 +84,10 @@ class CWKNN:
 
         adv_data = ori_data.clone().detach() + torch.randn((B, 3, K)).cuda() * 1e-7
         adv_data.requires_grad_()
+        # the kNN term sees a cloud that moves by a learning-rate step per iteration: seed its thresholds from the
+        # previous iteration's neighbours (same results, no spatial pre-pass; hitgeom.dist_utils.KNNDist.temporal_seeds)
+        if hasattr(self.dist_func, "temporal_seeds"):
+            self.dist_func.temporal_seeds(True)
         opt = optim.Adam([adv_data], lr=self.attack_lr, weight_decay=0., capturable=self.capturable_adam)
         stats = torch.zeros(3, device=adv_data.device)
         marks = max(self.num_iter // 5, 1)
