@@ -24,6 +24,7 @@ void hg_set_error(const char *fmt, ...);
     }                                 \
   } while (0)
 
+extern int g_hg_tune_knn_win;     // hg_tune("knn_win", n)
 extern int g_hg_tune_knn_tc_off;  // hg_tune("knn_tc", 1) switches the tensor-core kNN prefilter off
 extern int g_hg_tune_nn_exact;  // hg_tune("nn_exact", v), see hg_nn_bidir.cu
 extern int g_hg_tune_scatter;  // hg_tune("scatter", v): development knob, see hg_abi.cu
