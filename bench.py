@@ -621,6 +621,9 @@ def hitadv_record(rank, world, local, iters, warm_iters=5):
             gather_ms = None
             if timing.get("events") is not None:
                 gather_ms = sharding.max_over_ranks(timing["events"][0].elapsed_time(timing["events"][1]))
+            # the same gather again, ranks aligned by a barrier first (the figure above includes the wait for the
+            # slowest rank to finish its attack: arrival skew, not transfer time)
+            aligned = gather_record(adv_all[lo:hi].contiguous(), world, reps=2) if world > 1 else {}
             modes[tag] = {"ms_per_iteration": it_ms, "cloud_iterations_per_s": world * B / (it_ms * 1e-3),
                           "attack_iters_per_s_per_batch": 1e3 / it_ms,
                           "iterations_timed": int(att.replays) if graph else iters,
@@ -628,7 +631,8 @@ def hitadv_record(rank, world, local, iters, warm_iters=5):
                           "hitgeom_launches_per_iteration": int((_lib.launch_count() - launches0) // iters) if not graph else None,
                           "collective": {"op": "all_gather_into_tensor", "backend": "nccl" if world > 1 else "none (single rank)",
                                          "bytes_per_rank": timing.get("bytes_per_rank"), "bytes_total": timing.get("bytes_total"),
-                                         "ms": gather_ms, "gathered_clouds": int(adv_all.shape[0]),
+                                         "ms_incl_arrival_skew": gather_ms, "ms": aligned.get("ms"),
+                                         "busbw_gbs": aligned.get("busbw_gbs"), "gathered_clouds": int(adv_all.shape[0]),
                                          "counters_all_reduced": counters}}
         except Exception as e:  # noqa: BLE001 -- a failing mode is reported, the other one still counts
             modes[tag] = {"error": f"{type(e).__name__}: {e}"}

@@ -255,28 +255,95 @@ __device__ __forceinline__ float tc_exact_dist(const float *__restrict__ xi_s, c
                                                float xxj) {
   float acc = 0.f;
   const float4 *p = reinterpret_cast<const float4 *>(xj);
-#pragma unroll 4
-  for (int c = 0; c < C / 4; ++c) {
-    const float4 v = __ldg(p + c);
-    acc = __fmaf_rn(xi_s[4 * c], v.x, acc);
-    acc = __fmaf_rn(xi_s[4 * c + 1], v.y, acc);
-    acc = __fmaf_rn(xi_s[4 * c + 2], v.z, acc);
-    acc = __fmaf_rn(xi_s[4 * c + 3], v.w, acc);
+  const float4 *q = reinterpret_cast<const float4 *>(xi_s);
+  // 64 channels at a time: all sixteen 16-byte loads of the candidate row in flight before the (sequential) FMA chain
+  // starts -- the loop is bound by the latency of these L2 gathers, not by the chain
+#pragma unroll
+  for (int h = 0; h < C / 64 + (C % 64 ? 1 : 0); ++h) {
+    constexpr int kChunk = 16;
+    float4 v[kChunk];
+#pragma unroll
+    for (int c = 0; c < kChunk; ++c)
+      if (h * kChunk + c < C / 4) v[c] = __ldg(p + h * kChunk + c);
+#pragma unroll
+    for (int c = 0; c < kChunk; ++c)
+      if (h * kChunk + c < C / 4) {
+        const float4 a = q[h * kChunk + c];
+        acc = __fmaf_rn(a.x, v[c].x, acc);
+        acc = __fmaf_rn(a.y, v[c].y, acc);
+        acc = __fmaf_rn(a.z, v[c].z, acc);
+        acc = __fmaf_rn(a.w, v[c].w, acc);
+      }
   }
   return __fadd_rn(__fadd_rn(xxj, __fmul_rn(-2.0f, acc)), xxi);
 }
 
+// Exact -2*zz chains of the 32 candidates of one round (lane = candidate), with COALESCED gathers: read by their owner
+// lanes, 32 candidate rows are 32 different 128-byte lines per load instruction (the first version: 33.5 M L1
+// wavefronts per call, which is what bounded the kernel, not its FMA chains).  Here the warp loads whole rows together
+// -- sixteen lanes per 256-byte half-row pair, full lines -- stages them in shared memory (row stride padded by one
+// 16-byte chunk: conflict-free LDS.128 by the owners) and every lane then runs its chain out of shared memory,
+// 64 channels per stage.  Returns the lane's accumulator (the reference's sequential FMA chain over all C channels).
+constexpr int kStageChunks = 16;                   // 16-byte chunks of a candidate row per stage (64 channels)
+constexpr int kStageStride = kStageChunks + 1;     // in float4
 template <int C>
-__global__ void __launch_bounds__(128, 12) knn_tc_exact_kernel(const float *__restrict__ pc /*[nb,K,C] of this batch*/,
+__device__ __forceinline__ float tc_chain_staged(const float *__restrict__ xi_s, const float *__restrict__ cloud, int myj,
+                                                 float4 *__restrict__ stage /*[32][kStageStride]*/, int lane) {
+  float acc = 0.f;
+  const float4 *q4 = reinterpret_cast<const float4 *>(xi_s);
+  constexpr int R = C / 4;  // chunks per row
+#pragma unroll 1
+  for (int h0 = 0; h0 < R; h0 += kStageChunks) {
+    const int rh = (R - h0 < kStageChunks) ? (R - h0) : kStageChunks;  // chunks of this stage (8 or 16)
+    __syncwarp();
+    for (int g = lane; g < 32 * rh; g += 32) {  // chunk g of the stage: candidate g / rh, chunk g % rh
+      const int cq = g / rh, ch = g - cq * rh;
+      const int j = __shfl_sync(0xffffffffu, myj, cq);
+      stage[cq * kStageStride + ch] = __ldg(reinterpret_cast<const float4 *>(cloud + (size_t)j * C) + h0 + ch);
+    }
+    __syncwarp();
+    const float4 *mine = stage + lane * kStageStride;
+#pragma unroll 4
+    for (int c = 0; c < rh; ++c) {
+      const float4 a = q4[h0 + c], v = mine[c];
+      acc = __fmaf_rn(a.x, v.x, acc);
+      acc = __fmaf_rn(a.y, v.y, acc);
+      acc = __fmaf_rn(a.z, v.z, acc);
+      acc = __fmaf_rn(a.w, v.w, acc);
+    }
+  }
+  return acc;
+}
+
+// rank[u] = number of the row's candidate keys below mk[u] (broadcast 16-byte reads, two keys each; slots beyond NS idle)
+template <int NS>
+__device__ __forceinline__ void tc_rank(const unsigned long long *__restrict__ keys, int n,
+                                        const unsigned long long (&mk)[kTcCap / 32], int (&rank)[kTcCap / 32]) {
+  const ulonglong2 *k2 = reinterpret_cast<const ulonglong2 *>(keys);
+  int t = 0;
+  for (; t + 1 < n; t += 2) {
+    const ulonglong2 kk = k2[t >> 1];
+#pragma unroll
+    for (int u = 0; u < NS; ++u) rank[u] += (kk.x < mk[u] ? 1 : 0) + (kk.y < mk[u] ? 1 : 0);
+  }
+  if (t < n) {
+    const unsigned long long kt = keys[t];
+#pragma unroll
+    for (int u = 0; u < NS; ++u) rank[u] += kt < mk[u] ? 1 : 0;
+  }
+}
+
+template <int C>
+__global__ void __launch_bounds__(128, 6) knn_tc_exact_kernel(const float *__restrict__ pc /*[nb,K,C] of this batch*/,
                                                            const float *__restrict__ xx /*[nb,K]*/, int K, int k1,
                                                            int nrows, const int *__restrict__ cand,
                                                            const int *__restrict__ cnt, float *__restrict__ vals,
                                                            int *__restrict__ idx) {
-  extern __shared__ float esm[];  // per warp: x_i [C]
+  extern __shared__ __align__(16) float esm[];  // per warp: x_i [C], then the staging area [32][kStageStride] float4
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float *xi_s = esm + (size_t)warp * C;
-  __shared__ float cv[4][kTcCap];
-  __shared__ int ci[4][kTcCap];
+  float4 *stage = reinterpret_cast<float4 *>(esm + 4 * C) + (size_t)warp * 32 * kStageStride;
+  __shared__ __align__(16) unsigned long long ck[4][kTcCap];
   for (int r = blockIdx.x * 4 + warp; r < nrows; r += gridDim.x * 4) {
     const int bl = r / K;
     const float *cloud = pc + (size_t)bl * K * C;
@@ -288,50 +355,39 @@ __global__ void __launch_bounds__(128, 12) knn_tc_exact_kernel(const float *__re
     const float *xxb = xx + (size_t)bl * K;
     const int n = cnt[r];
     if (n <= kTcCap) {
-      float mv[kTcCap / 32];
-      int mj[kTcCap / 32];
-#pragma unroll
-      for (int u = 0; u < kTcCap / 32; ++u) {
-        mv[u] = CUDART_INF_F;
-        mj[u] = 0x7fffffff;
-      }
+      // exact distance of every listed candidate, as one sortable 64-bit key (order-preserving value bits, index)
       const int *crow = cand + (size_t)r * kTcCap;
-#pragma unroll 1  // one candidate per lane at a time: few registers, many resident warps (the loop is bound by the
-      for (int u = 0; u < kTcCap / 32; ++u) {  // latency of the candidates' L2 gathers, not by its FMA chains)
-        const int q = lane + 32 * u;
-        if (q < n) {
-          const int j = crow[q];
-          const float d = tc_exact_dist<C>(xi_s, cloud + (size_t)j * C, xxi, xxb[j]);
-          cv[warp][q] = d;
-          ci[warp][q] = j;
-        }
-      }
-      __syncwarp();
+      const int nslots = (n + 31) >> 5;  // warp-uniform
+      unsigned long long mk[kTcCap / 32];
 #pragma unroll
       for (int u = 0; u < kTcCap / 32; ++u) {
-        const int q = lane + 32 * u;
-        if (q < n) {
-          mv[u] = cv[warp][q];
-          mj[u] = ci[warp][q];
+        mk[u] = ~0ull;
+        if (u < nslots) {  // (warp-uniform)
+          const int q = lane + 32 * u;
+          const int j = crow[q < n ? q : 0];  // idle lanes shadow candidate 0 (valid memory), result discarded
+          const float acc = tc_chain_staged<C>(xi_s, cloud, j, stage, lane);
+          if (q < n) {
+            // reference formula; + 0.0f: a -0.0 would sort before +0.0 as a key although the two compare equal
+            const float d = __fadd_rn(__fadd_rn(__fadd_rn(xxb[j], __fmul_rn(-2.0f, acc)), xxi), 0.0f);
+            mk[u] = ((unsigned long long)hg_ord(d) << 32) | (unsigned)j;
+            ck[warp][q] = mk[u];
+          }
         }
       }
       __syncwarp();
-      // rank of every candidate among the row's candidates by (value, index): the ranks are a permutation, the
-      // candidates ranked below k1 are the answer, already in their output slots -- no selection rounds
+      // rank of every candidate among the row's candidates by (value, index): the keys are distinct, so the ranks are
+      // a permutation; the candidates ranked below k1 are the answer, already in their output slots
       int rank[kTcCap / 32];
 #pragma unroll
       for (int u = 0; u < kTcCap / 32; ++u) rank[u] = 0;
-      for (int t = 0; t < n; ++t) {
-        const float vt = cv[warp][t];  // broadcast reads
-        const int jt = ci[warp][t];
-#pragma unroll
-        for (int u = 0; u < kTcCap / 32; ++u) rank[u] += (vt < mv[u] || (vt == mv[u] && jt < mj[u])) ? 1 : 0;
-      }
+      if (nslots == 1) tc_rank<1>(ck[warp], n, mk, rank);
+      else if (nslots == 2) tc_rank<2>(ck[warp], n, mk, rank);
+      else tc_rank<3>(ck[warp], n, mk, rank);
 #pragma unroll
       for (int u = 0; u < kTcCap / 32; ++u)
-        if (lane + 32 * u < n && rank[u] < k1) {
-          if (vals) vals[(size_t)r * k1 + rank[u]] = mv[u];
-          idx[(size_t)r * k1 + rank[u]] = mj[u];
+        if (u < nslots && lane + 32 * u < n && rank[u] < k1) {
+          if (vals) vals[(size_t)r * k1 + rank[u]] = hg_unord((unsigned)(mk[u] >> 32));
+          idx[(size_t)r * k1 + rank[u]] = (int)(unsigned)(mk[u] & 0xffffffffu);
         }
     } else {
       // list overflow (heavy ties, degenerate features; rare): k1 rounds of "smallest (value, index) after the previous
@@ -400,10 +456,11 @@ int run_tc(const float *pc, const float *xx, float *xxmax, int B, int K, int k1,
   HG_REQUIRE(enc != nullptr, HG_E_UNSUPPORTED, "knn (tensor-core path): cuTensorMapEncodeTiled is not available");
   constexpr int NP = C / kTcPanelK;
   const size_t fsmem = (size_t)NP * (kTcRows + kTcTile) * 128 + (size_t)((K + kTcTile - 1) / kTcTile) * kTcTile * sizeof(float);
-  const size_t esmem = (size_t)4 * C * sizeof(float);
+  const size_t esmem = (size_t)4 * C * sizeof(float) + (size_t)4 * 32 * kStageStride * sizeof(float4);
   static HgPerDeviceOnce once;
   if (once.first()) {
     HG_CUDA(cudaFuncSetAttribute(knn_tc_filter_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    HG_CUDA(cudaFuncSetAttribute(knn_tc_exact_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
   }
   knn_tc_max_kernel<<<B, 256, 0, stream>>>(xx, K, xxmax);
   HG_CHECK_LAUNCH("knn_tc_max_kernel");
