@@ -79,7 +79,10 @@ SCRIPT = textwrap.dedent('''
     sys.modules["matplotlib.pyplot"].figure = lambda *a, **k: None
     from ShapeAttack.HiT_ADV import HiT_ADV as RefHiT
     from hitgeom.hit_adv import HiT_ADV
-    same_signature(RefHiT.__init__, HiT_ADV.__init__)
+    # the reference's parameters, in order, with its defaults; `graph=False` (CUDA-graph replay) is an optional extra
+    pr, pm_ = inspect.signature(RefHiT.__init__).parameters, inspect.signature(HiT_ADV.__init__).parameters
+    assert list(pm_)[:len(pr)] == list(pr) and list(pm_)[len(pr):] == ["graph"], (list(pr), list(pm_))
+    assert all(pr[k].default == pm_[k].default for k in pr) and pm_["graph"].default is False
     same_signature(RefHiT.attack, HiT_ADV.attack)
     import FGM.GeoA3_args as ref_geo                                        # -> pointnet2_ops_lib.pointnet2_ops.pointnet2_utils
     assert ref_geo.pointnet2_utils._ext is sys.modules["pointnet2_ops._ext"]
