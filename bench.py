@@ -295,10 +295,13 @@ def distance_record(workload, B, N, name, steps, warmup, rank, world, local, wit
     adv_d = adv_h.to(dev, non_blocking=True).requires_grad_()
     small = workload == "c1"
 
-    def make_fwd_bwd(temporal):
-        """temporal=True: the kNN term keeps last call's neighbour indices as seeds (what an attack loop does)."""
+    def make_fwd_bwd(temporal, overlap=False):
+        """temporal=True: the kNN term keeps last call's neighbour indices as seeds (what an attack loop does).
+        overlap=True (config 1): the kNN term, which does not depend on the other two, is enqueued on a forked stream
+        (hitgeom.overlap.side_branch) -- at 388 x 1024 no single kernel fills 148 SMs."""
         if small:
             from hitgeom.dist_utils import shared_distance_pass
+            from hitgeom.overlap import side_branch
 
             cd, hd, kd = ChamferDist(), HausdorffDist(), KNNDist(k=5).temporal_seeds(temporal)
 
@@ -308,7 +311,12 @@ def distance_record(workload, B, N, name, steps, warmup, rank, world, local, wit
                 else:
                     adv_d.grad = None
                 with shared_distance_pass():  # Chamfer and Hausdorff of the same pair: one distance pass
-                    loss = cd(adv_d, ori_d) + hd(adv_d, ori_d) + kd(adv_d)
+                    if overlap:
+                        with side_branch() as br:
+                            l_knn = kd(adv_d)
+                        loss = cd(adv_d, ori_d) + hd(adv_d, ori_d) + br.join(l_knn)
+                    else:
+                        loss = cd(adv_d, ori_d) + hd(adv_d, ori_d) + kd(adv_d)
                 loss.backward()
                 return loss
         else:
@@ -324,7 +332,8 @@ def distance_record(workload, B, N, name, steps, warmup, rank, world, local, wit
                 return loss
         return fn
 
-    fwd_bwd = make_fwd_bwd(False)
+    fwd_bwd = make_fwd_bwd(False, overlap=small)
+    fwd_bwd_serial = make_fwd_bwd(False) if small else fwd_bwd
 
     pairs_step = B * pairs_per_cloud(N)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if small else None
@@ -338,7 +347,7 @@ def distance_record(workload, B, N, name, steps, warmup, rank, world, local, wit
     for _ in range(max(warmup, 3)):
         fwd_bwd()
     torch.cuda.synchronize()
-    step, eager_ms = fwd_bwd, None
+    step, eager_ms, serial_ms = fwd_bwd, None, None
     if small:
         # config 1 is ~0.3 ms of kernel work behind ~25 launches: launch-bound.  An attack loop replays the step as a
         # CUDA graph (hitgeom.cw_knn graph=True); time that, and report the eager figure next to it.
@@ -359,6 +368,18 @@ def distance_record(workload, B, N, name, steps, warmup, rank, world, local, wit
 
         graph, graph_loss = capture(fwd_bwd)
         torch.cuda.synchronize()
+        # the same step with the three terms on ONE stream, for the record
+        graph_serial, _ = capture(fwd_bwd_serial)
+        torch.cuda.synchronize()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(max(steps, 10))]
+        for s_, e_ in evs:
+            l2_flush()
+            s_.record()
+            graph_serial.replay()
+            e_.record()
+        torch.cuda.synchronize()
+        serial_ms = sum(s_.elapsed_time(e_) for s_, e_ in evs) / len(evs)
+        del graph_serial
         for _ in range(3):  # (the capture left the caching allocator in a new state: warm the eager path again)
             fwd_bwd()
         torch.cuda.synchronize()
@@ -400,11 +421,11 @@ def distance_record(workload, B, N, name, steps, warmup, rank, world, local, wit
         launches = _lib.launch_count() - l0
     ms_local = sum(s.elapsed_time(e) for s, e in evs) / steps
     ms = sharding.max_over_ranks(ms_local)
-    if eager_ms is not None:  # the per-kernel event hooks only fire on eager launches
+    if eager_ms is not None:  # the per-kernel event hooks only fire on eager launches; one stream: kernels timed alone
         _lib.prof_enable(True)
         for _ in range(steps):
             l2_flush()
-            fwd_bwd()
+            fwd_bwd_serial()
         torch.cuda.synchronize()
     nn_ms, nn_n = _lib.prof_read("nn_bidir")
     knn_ms, knn_n = _lib.prof_read("knn")
@@ -415,7 +436,7 @@ def distance_record(workload, B, N, name, steps, warmup, rank, world, local, wit
     # ---- the same step with temporal kNN seeds (attack-loop usage: KNNDist.temporal_seeds) -----------------------
     temporal = None
     try:
-        fb_t = make_fwd_bwd(True)
+        fb_t = make_fwd_bwd(True, overlap=small)
         for _ in range(3):
             fb_t()
         if small:
@@ -526,7 +547,7 @@ def distance_record(workload, B, N, name, steps, warmup, rank, world, local, wit
                 "peak_gbs": pk.get("hbm_gbs"), "peak_source": pk_src},
     }
     rec = {"value": world * pairs_step / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
-           "config": distance_config(workload, B, N, name, eager_ms), "clocks": clocks, "roofline": roofline,
+           "config": distance_config(workload, B, N, name, eager_ms, serial_ms), "clocks": clocks, "roofline": roofline,
            "parity_check": parity, "gpu_launches": int(launches), "temporal_seeds": temporal}
     if e2e is not None:
         rec["e2e"] = e2e
@@ -534,16 +555,19 @@ def distance_record(workload, B, N, name, steps, warmup, rank, world, local, wit
     return rec
 
 
-def distance_config(workload, B, N, name, eager_ms=None):
+def distance_config(workload, B, N, name, eager_ms=None, serial_ms=None):
     cfg = {"workload": name, "clouds_per_gpu": B, "points": N, "k": 5,
            "l2": ("L2 flushed (256 MiB write + 256 MiB read) between timed iterations" if workload == "c1" else
                   f"inputs ({B * N * 24 / 1e6:.0f} MB/rank) exceed the 126 MB L2" if B * N * 24 > 126e6 else
                   "inputs fit in L2 (not flushed)"),
            "pair_evals_per_step_per_gpu": B * pairs_per_cloud(N)}
     if workload == "c1":
-        cfg["replay"] = "step replayed as one CUDA graph"
+        cfg["replay"] = ("step replayed as one CUDA graph; the kNN term is enqueued on a forked stream "
+                         "(hitgeom.overlap.side_branch) and captured as a parallel arm of the graph")
         if eager_ms is not None:
             cfg["eager_ms_per_step"] = eager_ms
+        if serial_ms is not None:
+            cfg["one_stream_graph_ms_per_step"] = serial_ms
     return cfg
 
 

@@ -39,6 +39,10 @@ HG_API int hg_tune(const char *key, int value) {
     g_hg_tune_nn_exact = value;
     return HG_OK;
   }
+  if (!strcmp(key, "small_fused")) {  // 1 = small clouds use the general (multi-kernel) finish / kNN-backward paths
+    g_hg_tune_small_fused_off = value;
+    return HG_OK;
+  }
   hg_set_error("hg_tune: unknown key '%s'", key);
   return HG_E_BADARG;
 }

@@ -375,6 +375,118 @@ __global__ void __launch_bounds__(256) knn_outlier_bwd_kernel(const float *__res
   }
 }
 
+// Small 3-D clouds: the whole backward of one cloud in ONE CTA -- keys, reverse map (integer shared-memory atomics:
+// counts and slots are order-independent, the walk below is in ascending edge order whatever the slots) and the
+// gradient -- instead of keys + memset + count + scan + fill + gradient kernels (53 us of a 385 us config-1 step).
+// Same sums in the same order as knn_outlier_bwd_kernel.
+constexpr int kBwdSmallSmemMax = 100 * 1024;
+__host__ __device__ inline size_t knn_bwd_small_smem(int K, int k1) {
+  return ((size_t)K * 3 + (size_t)K + (size_t)(K + 1) + (size_t)K + (size_t)K * (k1 - 1)) * 4;
+}
+
+__global__ void __launch_bounds__(256) knn_outlier_bwd_small_kernel(const float *__restrict__ pc,
+                                                                    const int *__restrict__ idx,
+                                                                    const float *__restrict__ mask,
+                                                                    const float *__restrict__ g, int K, int k1,
+                                                                    float *__restrict__ grad) {
+  extern __shared__ int bsm[];
+  float *sp = (float *)bsm;              // [K*3]
+  float *smask = sp + (size_t)K * 3;     // [K]
+  int *soff = (int *)(smask + K);        // [K+1]
+  int *scur = soff + K + 1;              // [K]
+  int *slist = scur + K;                 // [<= K*(k1-1)]
+  __shared__ int warp_tot[8];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float *p = pc + (size_t)b * K * 3;
+  const int *ix = idx + (size_t)b * K * k1;
+  for (int q = tid; q < K * 3; q += 256) sp[q] = p[q];
+  for (int q = tid; q < K; q += 256) smask[q] = mask[(size_t)b * K + q];
+  for (int q = tid; q <= K; q += 256) soff[q] = 0;
+  __syncthreads();
+  // edges leave outlier rows only (mask != 0, a few per cent of the cloud): walk rows, not edges
+  auto key_at = [&](int i, int t) -> int {
+    const int key = ix[(size_t)i * k1 + t];
+    return (key >= 0 && key < K) ? key : -1;
+  };
+  for (int i = tid; i < K; i += 256)
+    if (smask[i] != 0.f)
+      for (int t = 1; t < k1; ++t) {
+        const int key = key_at(i, t);
+        if (key >= 0) atomicAdd(soff + key + 1, 1);
+      }
+  __syncthreads();
+  {  // exclusive scan of the counts: contiguous chunk per thread, warp scan, block carry
+    const int per = (K + 255) / 256;
+    const int lo = min(tid * per, K), hi = min(lo + per, K);
+    int sum = 0;
+    for (int i = lo; i < hi; ++i) sum += soff[i + 1];
+    int v = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, v, d);
+      if (lane >= d) v += t;
+    }
+    if (lane == 31) warp_tot[warp] = v;
+    __syncthreads();
+    int run = v - sum;
+    for (int w = 0; w < warp; ++w) run += warp_tot[w];
+    for (int i = lo; i < hi; ++i) {
+      const int c = soff[i + 1];
+      scur[i] = run;
+      run += c;
+      soff[i + 1] = run;  // (soff[0] stays 0)
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < K; i += 256)
+    if (smask[i] != 0.f)
+      for (int t = 1; t < k1; ++t) {
+        const int key = key_at(i, t);
+        if (key >= 0) slist[atomicAdd(scur + key, 1)] = i * k1 + t;
+      }
+  __syncthreads();
+  const float coef = g[b] / ((float)K * (float)(k1 - 1));
+  for (int n = tid; n < K; n += 256) {
+    const float v0 = sp[n * 3], v1 = sp[n * 3 + 1], v2 = sp[n * 3 + 2];
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    if (smask[n] != 0.f) {
+      const int *nb = ix + (size_t)n * k1;
+      for (int t = 1; t < k1; ++t) {
+        const float *r = sp + (size_t)nb[t] * 3;
+        a0 += 2.0f * (v0 - r[0]);
+        a1 += 2.0f * (v1 - r[1]);
+        a2 += 2.0f * (v2 - r[2]);
+      }
+    }
+    const int p0 = soff[n], p1 = soff[n + 1];
+    if (p1 - p0 <= 32) {
+      int e = -1;
+      for (int q = p0; q < p1; ++q) {
+        e = hg_csr_next(slist, p0, p1, e);
+        const float *r = sp + (size_t)(e / k1) * 3;
+        a0 += 2.0f * (v0 - r[0]);
+        a1 += 2.0f * (v1 - r[1]);
+        a2 += 2.0f * (v2 - r[2]);
+      }
+    } else {  // a hub: scan the forward map (ascending edge order = rows, then slots)
+      for (int i = 0; i < K; ++i) {
+        if (smask[i] == 0.f) continue;
+        for (int t = 1; t < k1; ++t)
+          if (key_at(i, t) == n) {
+            const float *r = sp + (size_t)i * 3;
+            a0 += 2.0f * (v0 - r[0]);
+            a1 += 2.0f * (v1 - r[1]);
+            a2 += 2.0f * (v2 - r[2]);
+          }
+      }
+    }
+    float *go = grad + ((size_t)b * K + n) * 3;
+    go[0] = coef * a0;
+    go[1] = coef * a1;
+    go[2] = coef * a2;
+  }
+}
+
 int grid_for(long long total, int threads) {
   long long blocks = (total + threads - 1) / threads;
   const long long cap = (long long)hg_sm_count() * 16;
@@ -478,6 +590,15 @@ HG_API int hg_knn_outlier_bwd_f32(const float *pc, const int *idx, const float *
   HG_REQUIRE(B > 0 && K > 1 && C > 0 && k1 >= 2, HG_E_BADARG, "knn_outlier_bwd: bad sizes");
   HG_REQUIRE(workspace && workspace_bytes >= hg_knn_outlier_bwd_workspace_bytes(B, K, k1), HG_E_WORKSPACE,
              "knn_outlier_bwd: workspace too small");
+  if (C == 3 && knn_bwd_small_smem(K, k1) <= (size_t)kBwdSmallSmemMax && !g_hg_tune_small_fused_off) {
+    static HgPerDeviceOnce once;
+    if (once.first())
+      HG_CUDA(cudaFuncSetAttribute(knn_outlier_bwd_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   kBwdSmallSmemMax));
+    knn_outlier_bwd_small_kernel<<<B, 256, knn_bwd_small_smem(K, k1), stream>>>(pc, idx, mask, g, K, k1, grad_pc);
+    HG_CHECK_LAUNCH("knn_outlier_bwd_small_kernel");
+    return HG_OK;
+  }
   int *keys = (int *)workspace;
   void *csr_ws = (char *)workspace + hg_align((size_t)B * K * k1 * sizeof(int));
   const long long total = (long long)B * K * k1;

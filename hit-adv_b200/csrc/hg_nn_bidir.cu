@@ -32,6 +32,7 @@ namespace {
 
 constexpr int kCsrWalkMax = 32;  // in-degree up to which the backward walks a reverse-map segment by selection
 constexpr int kColBatch = 32;  // rows per column-direction tracking batch (and rescan width of the finish kernel)
+constexpr int kFinishSmallSmemMax = 100 * 1024;  // both clouds of a pair in shared memory: the small finish kernel
 
 struct NnParams {
   const float *gts;    // [B,N2,3]
@@ -271,6 +272,131 @@ __global__ void __launch_bounds__(256) nn_bidir_d3_finish_kernel(NnParams p, int
       arg2[(size_t)b * p.N2 + i] = arg;
     }
   }
+}
+
+// Small clouds (each fits in shared memory): a CTA stages ONE cloud as padded structure-of-arrays and re-scans either
+// 256 column entries against the rows (the 32-row batch of an entry split over FOUR lanes, 8 rows each, first match per
+// lane, quad minimum) or 1024 row entries against the columns (T columns per entry): 8 or T evaluations per thread and
+// iteration, four iterations, the four keys loaded up front.  The gather version above issues up to 96 scalar global
+// loads per column entry and is latency-bound at 1024 points (26 us at 388 x 1024, a quarter of the main kernel).
+// Same arithmetic, same first-index rule.
+constexpr int kFinColsPerCta = 256, kFinRowsPerCta = 1024;
+
+template <int T>
+__global__ void __launch_bounds__(256) nn_bidir_d3_finish_small_kernel(NnParams p, int ncolcta, float *__restrict__ min1,
+                                                                        int *__restrict__ arg1, float *__restrict__ min2,
+                                                                        int *__restrict__ arg2) {
+  constexpr int kTShift = T == 16 ? 4 : 3;
+  extern __shared__ float fsm[];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int N1 = p.N1, N2 = p.N2;
+  const float *gx = p.gts + (size_t)b * N2 * 3;
+  const float *gy = p.preds + (size_t)b * N1 * 3;
+  if ((int)blockIdx.y < ncolcta) {
+    // rows staged; pad one slot per 32 (a quad walks the rows of ITS batch; batches differ between quads)
+    const int xs = N2 + (N2 >> 5) + 1;
+    float *sx0 = fsm, *sx1 = fsm + xs, *sx2 = fsm + 2 * xs;
+    const int jbase = blockIdx.y * kFinColsPerCta;
+    unsigned long long key[4];
+    float y0[4], y1[4], y2[4];
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int j = jbase + ((it * 256 + tid) >> 2);
+      key[it] = 0ull;
+      y0[it] = y1[it] = y2[it] = 0.f;
+      if (j < N1) {
+        key[it] = p.colres[(size_t)b * N1 + j];
+        y0[it] = __ldg(gy + (size_t)j * 3);
+        y1[it] = __ldg(gy + (size_t)j * 3 + 1);
+        y2[it] = __ldg(gy + (size_t)j * 3 + 2);
+      }
+    }
+    for (int q = tid; q < N2 * 3; q += 256) {
+      const int i = q / 3, c = q - 3 * i;
+      fsm[c * xs + i + (i >> 5)] = __ldg(gx + q);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int u = it * 256 + tid, j = jbase + (u >> 2), part = u & 3;
+      const bool live = j < N1;
+      const float m = hg_unord((unsigned)(key[it] >> 32));
+      int arg = 0x7fffffff;
+      if (live) {
+        const int i0 = (int)(unsigned)(key[it] & 0xffffffffu) * kColBatch + part * 8;
+#pragma unroll
+        for (int d = 7; d >= 0; --d) {  // descending: the smallest matching row is what stays
+          const int i = i0 + d;
+          if (i < N2) {
+            const int ii = i + (i >> 5);
+            if (nn_p_exact(sx0[ii], sx1[ii], sx2[ii], y0[it], y1[it], y2[it]) == m) arg = i;
+          }
+        }
+      }
+      arg = min(arg, __shfl_xor_sync(0xffffffffu, arg, 1));
+      arg = min(arg, __shfl_xor_sync(0xffffffffu, arg, 2));
+      if (live && part == 0) {
+        min1[(size_t)b * N1 + j] = m;
+        arg1[(size_t)b * N1 + j] = arg == 0x7fffffff ? 0 : arg;
+      }
+    }
+  } else {
+    // columns staged; pad one slot per T (a row entry walks the T columns of its lane; lanes differ by T)
+    const int ys = N1 + (N1 >> kTShift) + 1;
+    float *sy0 = fsm, *sy1 = fsm + ys, *sy2 = fsm + 2 * ys;
+    const int ibase = ((int)blockIdx.y - ncolcta) * kFinRowsPerCta;
+    unsigned long long key[4];
+    float x0[4], x1[4], x2[4];
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int i = ibase + it * 256 + tid;
+      key[it] = 0ull;
+      x0[it] = x1[it] = x2[it] = 0.f;
+      if (i < N2) {
+        key[it] = p.rowres[(size_t)b * N2 + i];
+        x0[it] = __ldg(gx + (size_t)i * 3);
+        x1[it] = __ldg(gx + (size_t)i * 3 + 1);
+        x2[it] = __ldg(gx + (size_t)i * 3 + 2);
+      }
+    }
+    for (int q = tid; q < N1 * 3; q += 256) {
+      const int j = q / 3, c = q - 3 * j;
+      fsm[c * ys + j + (j >> kTShift)] = __ldg(gy + q);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int i = ibase + it * 256 + tid;
+      if (i >= N2) continue;
+      const float m = hg_unord((unsigned)(key[it] >> 32));
+      const unsigned code = (unsigned)(key[it] & 0xffffffffu);
+      const int j0 = (int)(code >> 5) * 32 * T + (int)(code & 31u) * T;
+      int arg = 0;
+#pragma unroll
+      for (int d = T - 1; d >= 0; --d) {
+        const int j = j0 + d;
+        if (j < N1) {
+          const int jj = j + (j >> kTShift);
+          if (nn_p_exact(x0[it], x1[it], x2[it], sy0[jj], sy1[jj], sy2[jj]) == m) arg = j;
+        }
+      }
+      min2[(size_t)b * N2 + i] = m;
+      arg2[(size_t)b * N2 + i] = arg;
+    }
+  }
+}
+
+template <int T>
+static int launch_finish_small(const NnParams &p, int B, float *min1, int *arg1, float *min2, int *arg2, size_t smem,
+                               cudaStream_t stream) {
+  static HgPerDeviceOnce once;
+  if (once.first())
+    HG_CUDA(cudaFuncSetAttribute(nn_bidir_d3_finish_small_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 kFinishSmallSmemMax));
+  const int ncol = (p.N1 + kFinColsPerCta - 1) / kFinColsPerCta, nrow = (p.N2 + kFinRowsPerCta - 1) / kFinRowsPerCta;
+  nn_bidir_d3_finish_small_kernel<T><<<dim3(B, ncol + nrow), 256, smem, stream>>>(p, ncol, min1, arg1, min2, arg2);
+  HG_CHECK_LAUNCH("nn_bidir_d3_finish_small_kernel");
+  return HG_OK;
 }
 
 // ================================================================================================================
@@ -826,6 +952,7 @@ static int g_force_T = 0, g_force_RB = 0;
 // entries are near-ties at that density and their exact re-scans cost more than the loop saves (whole call 80 ms
 // against 57 ms; profiles/r02_experiment_nn_approx_tracker.txt).  Kept, tested bit for bit, as the measured experiment.
 int g_hg_tune_nn_exact = 1;
+int g_hg_tune_small_fused_off = 0;
 HG_API void hg_nn_bidir_tune(int T, int RB) {
   g_force_T = T;
   g_force_RB = RB;
@@ -924,6 +1051,14 @@ HG_API int hg_nn_bidir_f32(const float *gts, const float *preds, int B, int N2, 
     nn_resolve_kernel<<<hg_sm_count() * 4, 128, 0, stream>>>(p, min1, arg1, min2, arg2);
     HG_CHECK_LAUNCH("nn_resolve_kernel");
     return HG_OK;
+  }
+  {
+    const int tshift = T == 16 ? 4 : 3;
+    const size_t sx = (size_t)(N2 + (N2 >> 5) + 1), sy = (size_t)(N1 + (N1 >> tshift) + 1);
+    const size_t smem = 3 * (sx > sy ? sx : sy) * sizeof(float);
+    if (smem <= (size_t)kFinishSmallSmemMax && B <= 65535 && !g_hg_tune_small_fused_off)
+      return T == 16 ? launch_finish_small<16>(p, B, min1, arg1, min2, arg2, smem, stream)
+                     : launch_finish_small<8>(p, B, min1, arg1, min2, arg2, smem, stream);
   }
   if (T == 16)
     nn_bidir_d3_finish_kernel<16><<<grid_for(total, 256), 256, 0, stream>>>(p, B, min1, arg1, min2, arg2);

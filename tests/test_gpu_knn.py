@@ -39,8 +39,19 @@ def test_knn_self_vs_oracle(oracle, F, B, K, k1, kind):
     assert np.array_equal(idx.cpu().numpy(), oi)
 
 
+@pytest.fixture(params=["fused-small-backward", "general-backward"])
+def bwd_path(request):
+    """KNNDist's backward for 3-D clouds that fit in shared memory is one fused kernel (knn_outlier_bwd_small_kernel);
+    hg_tune("small_fused", 1) sends the same call down the general keys + reverse-map + gradient kernels."""
+    from hitgeom._lib import lib
+
+    lib().hg_tune(b"small_fused", 0 if request.param == "fused-small-backward" else 1)
+    yield request.param
+    lib().hg_tune(b"small_fused", 0)
+
+
 @pytest.mark.parametrize("k,alpha", [(5, 1.05), (4, 1.05), (8, 0.5)])
-def test_knn_dist_golden(golden, k, alpha):
+def test_knn_dist_golden(golden, k, alpha, bwd_path):
     from hitgeom.dist_utils import KNNDist
 
     g = golden("loss_classes")
@@ -56,7 +67,7 @@ def test_knn_dist_golden(golden, k, alpha):
             assert np.abs(gr - ref).max() <= 1e-5 * np.abs(ref).max(), key
 
 
-def test_knn_dist_vs_oracle_config1(oracle):
+def test_knn_dist_vs_oracle_config1(oracle, bwd_path):
     """Config 1 shape (388 x 1024): loss and gradient against the oracle."""
     from hitgeom.dist_utils import KNNDist
 
@@ -159,7 +170,7 @@ def test_knn_generic_c_heavy_ties(oracle, F):
     assert np.array_equal(vals.cpu().numpy(), ov) and np.array_equal(idx.cpu().numpy(), oi)
 
 
-def test_knn_outlier_backward_with_hub_points_vs_oracle(oracle):
+def test_knn_outlier_backward_with_hub_points_vs_oracle(oracle, bwd_path):
     """Padding by repetition: hundreds of points coincide, so a few points are the neighbour of hundreds of others
     (in-degree far above the 32 the selection walk handles): the gradient is still the oracle's, promptly."""
     import time
@@ -181,6 +192,25 @@ def test_knn_outlier_backward_with_hub_points_vs_oracle(oracle):
     np.testing.assert_allclose(loss.detach().cpu().numpy(), ol, rtol=1e-6, atol=1e-12)
     # (sums of hundreds of terms: 1e-4, see test_backward_with_hub_points_vs_oracle)
     assert normwise(a.grad.cpu().numpy(), oracle.knn_outlier_bwd(pc, idx, mask, np.ones(2, np.float32))) < 1e-4
+
+
+def test_knn_outlier_backward_fused_and_general_paths_give_the_same_bits():
+    """Both backward paths add the same terms in the same (ascending edge) order: identical gradients, hubs included."""
+    from hitgeom._lib import lib
+    from hitgeom.dist_utils import KNNDist
+
+    pc = jitter(clouds(24, 1024, 77), 5)
+    pc[3, 200:420] = pc[3, 7]
+    grads = []
+    for off in (0, 1):
+        lib().hg_tune(b"small_fused", off)
+        try:
+            a = gpu(pc).requires_grad_()
+            KNNDist(k=5, alpha=0.3)(a, batch_avg=False).sum().backward()
+            grads.append(a.grad.clone())
+        finally:
+            lib().hg_tune(b"small_fused", 0)
+    assert grads[0].abs().max() > 0 and torch.equal(grads[0], grads[1])
 
 
 # ---- tensor-core prefilter (hg_knn_tc.cu): same values and indices as the FP32 path and the oracle --------------------

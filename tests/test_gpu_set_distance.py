@@ -21,16 +21,19 @@ def F():
     return functional
 
 
-@pytest.fixture(autouse=True, params=["approx-tracker", "exact-tracker"])
+@pytest.fixture(autouse=True, params=["approx-tracker", "exact-tracker", "exact-tracker-gather-finish"])
 def _tracker(request):
-    """Every test of this module runs twice: with the default distance pass (5-operation exact tracker) and with the
-    experimental 4-operation approximate tracker + exact recovery in the finish kernels (hg_tune("nn_exact", 0),
-    hg_nn_bidir.cu).  Both must give the reference's bits."""
+    """Every test of this module runs three times: with the default distance pass (5-operation exact tracker; clouds
+    that fit in shared memory finish in nn_bidir_d3_finish_small_kernel), with the general gather finish kernel forced
+    for small clouds too (hg_tune("small_fused", 1)), and with the experimental 4-operation approximate tracker + exact
+    recovery in the finish kernels (hg_tune("nn_exact", 0), hg_nn_bidir.cu).  All must give the reference's bits."""
     from hitgeom._lib import lib
 
-    lib().hg_tune(b"nn_exact", 1 if request.param == "exact-tracker" else 0)
+    lib().hg_tune(b"nn_exact", 0 if request.param == "approx-tracker" else 1)
+    lib().hg_tune(b"small_fused", 1 if request.param == "exact-tracker-gather-finish" else 0)
     yield request.param
     lib().hg_tune(b"nn_exact", 1)
+    lib().hg_tune(b"small_fused", 0)
 
 
 @pytest.mark.parametrize("name", ["setdist_eq", "setdist_ragged", "setdist_dups"])
