@@ -580,12 +580,25 @@ __global__ void __launch_bounds__(TH) fps_kernel(const float *__restrict__ datas
       low[r] = valid ? ~comp : 0u;
     }
   }
+  // One round = distance update of the register-resident points, then a block-wide lexicographic maximum of
+  // (distance bits, tie composite) with the winner's COORDINATES travelling with its key: the round's critical path has
+  // no dependent global load and no index decode (the raw composites are decoded by all threads after the last round).
+  // The round is one latency chain, so it is kept shallow (tools/ubench/redux_latency.cu on a B200: CREDUX round trip
+  // 27 cycles, a 64-bit shuffle butterfly 195, BAR.SYNC 21, dependent LDS 43): per level, a max tree + CREDUX over the
+  // distance bits, then the same over the composites of the entries that hold that distance, then predicated moves;
+  // clouds up to 2048 points run on one warp per scheduler.  A point that can never be selected has composite 0 and
+  // distance 0 for ever ("nothing" = composite 0).
+  static_assert(W <= 32, "one lane per warp in the second reduction level");
+  __shared__ float4 wcoord[2][W];
+#pragma unroll
+  for (int r = 0; r < PPT; ++r)
+    if (!low[r]) td[r] = 0.f;
   int old = (POLICY == POLICY_P2) ? 0 : (int)start[b];
   if (tid == 0) idxs[0] = (IdxT)old;
+  float x1 = __ldg(dataset + (size_t)old * 3), y1 = __ldg(dataset + (size_t)old * 3 + 1),
+        z1 = __ldg(dataset + (size_t)old * 3 + 2);
   for (int j = 1; j < m; ++j) {
-    const float x1 = __ldg(dataset + (size_t)old * 3), y1 = __ldg(dataset + (size_t)old * 3 + 1),
-                z1 = __ldg(dataset + (size_t)old * 3 + 2);
-    unsigned long long best = 0ull;
+    unsigned t[PPT];
 #pragma unroll
     for (int r = 0; r < PPT; ++r) {
       float d;
@@ -595,39 +608,88 @@ __global__ void __launch_bounds__(TH) fps_kernel(const float *__restrict__ datas
         const float dx = __fsub_rn(px[r], x1), dy = __fsub_rn(py[r], y1), dz = __fsub_rn(pz[r], z1);
         d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
       }
-      if (low[r]) {
-        td[r] = fminf(d, td[r]);
-        // distances are >= 0, so their bit patterns order like unsigned integers; +1 keeps key 0 = "nothing"
-        const unsigned long long key = ((unsigned long long)(__float_as_uint(td[r]) + 1u) << 32) | low[r];
-        best = key > best ? key : best;
-      }
+      td[r] = fminf(d, td[r]);
+      t[r] = __float_as_uint(td[r]);  // distances are >= 0: their bit patterns order like unsigned integers
     }
 #pragma unroll
-    for (int s = 16; s > 0; s >>= 1) {
-      const unsigned long long o = __shfl_xor_sync(0xffffffffu, best, s);
-      best = o > best ? o : best;
+    for (int s = 1; s < PPT; s <<= 1)
+#pragma unroll
+      for (int r = 0; r + s < PPT; r += 2 * s) t[r] = max(t[r], t[r + s]);
+    const unsigned whi = __reduce_max_sync(0xffffffffu, t[0]);
+#pragma unroll
+    for (int r = 0; r < PPT; ++r) t[r] = __float_as_uint(td[r]) == whi ? low[r] : 0u;
+#pragma unroll
+    for (int s = 1; s < PPT; s <<= 1)
+#pragma unroll
+      for (int r = 0; r + s < PPT; r += 2 * s) t[r] = max(t[r], t[r + s]);
+    const unsigned wlo = __reduce_max_sync(0xffffffffu, t[0]);
+    // one lane per warp: the composites are distinct; a warp with nothing to offer writes composite 0 from lane 0
+    if (t[0] == wlo && (wlo != 0u || lane == 0)) {
+      float bx = 0.f, by = 0.f, bz = 0.f;
+#pragma unroll
+      for (int r = 0; r < PPT; ++r)
+        if (__float_as_uint(td[r]) == whi && low[r] == wlo) {
+          bx = px[r];
+          by = py[r];
+          bz = pz[r];
+        }
+      wbest[j & 1][warp] = ((unsigned long long)whi << 32) | wlo;
+      wcoord[j & 1][warp] = make_float4(bx, by, bz, 0.f);
     }
-    if (lane == 0) wbest[j & 1][warp] = best;
     __syncthreads();
-    unsigned long long all = wbest[j & 1][0];
+    unsigned ahi, alo;
+    float4 c;
+    if (W <= 8) {  // few warps: every thread reads all (key, coordinates) pairs at once
+      unsigned long long k[W];
+      float4 kc[W];
 #pragma unroll
-    for (int w = 1; w < W; ++w) {
-      const unsigned long long o = wbest[j & 1][w];
-      all = o > all ? o : all;
-    }
-    if (all == 0ull) {
-      old = 0;
+      for (int w = 0; w < W; ++w) {
+        k[w] = wbest[j & 1][w];
+        kc[w] = wcoord[j & 1][w];
+      }
+      ahi = 0u;
+#pragma unroll
+      for (int w = 0; w < W; ++w) ahi = max(ahi, (unsigned)(k[w] >> 32));
+      alo = 0u;
+#pragma unroll
+      for (int w = 0; w < W; ++w) alo = max(alo, (unsigned)(k[w] >> 32) == ahi ? (unsigned)k[w] : 0u);
+      c = kc[0];
+#pragma unroll
+      for (int w = 1; w < W; ++w)
+        if ((unsigned)(k[w] >> 32) == ahi && (unsigned)k[w] == alo) c = kc[w];
     } else {
-      const unsigned comp = ~(unsigned)(all & 0xffffffffull);
+      const unsigned long long mine = lane < W ? wbest[j & 1][lane] : 0ull;
+      const unsigned mhi = (unsigned)(mine >> 32), mlo = (unsigned)mine;
+      ahi = __reduce_max_sync(0xffffffffu, mhi);
+      alo = __reduce_max_sync(0xffffffffu, mhi == ahi ? mlo : 0u);
+      const int wwin = __ffs(__ballot_sync(0xffffffffu, lane < W && mhi == ahi && mlo == alo)) - 1;
+      c = wcoord[j & 1][wwin];
+    }
+    if (alo == 0u) {  // no selectable point at all: the reference keeps writing index 0
+      x1 = __ldg(dataset);
+      y1 = __ldg(dataset + 1);
+      z1 = __ldg(dataset + 2);
+    } else {
+      x1 = c.x;
+      y1 = c.y;
+      z1 = c.z;
+    }
+    if (tid == 0) idxs[j] = (IdxT)(alo == 0u ? 0xffffffffu : ~alo);  // raw composite, decoded below
+  }
+  __syncthreads();
+  for (int j = 1 + tid; j < m; j += TH) {
+    const unsigned comp = (unsigned)idxs[j];
+    int out = 0;
+    if (comp != 0xffffffffu) {
       if (POLICY == POLICY_P2) {
         const unsigned rev = comp / R, rr = comp % R;
         const unsigned tb = log2bs ? (__brev(rev) >> (32 - log2bs)) : 0u;
-        old = (int)(tb + (rr << log2bs));
+        out = (int)(tb + (rr << log2bs));
       } else {
-        old = (int)comp;
+        out = (int)comp;
       }
     }
-    if (tid == 0) idxs[j] = (IdxT)old;
+    idxs[j] = (IdxT)out;
   }
 }
 
@@ -638,7 +700,10 @@ int launch_fps(const float *dataset, int b, int n, int m, const long long *start
     const int bs = ref_opt_n_threads(n);
     while ((1 << log2bs) < bs) ++log2bs;
   }
-  const int th = n > 4096 ? 1024 : 256;
+  // threads per cloud: the round is a latency chain (update -> warp max -> barrier -> block max), so small clouds run
+  // on ONE warp per scheduler (128 threads, <= 8 points per thread) and do not contend for issue slots
+  int th = n > 4096 ? 1024 : (n > 2048 ? 256 : 128);
+  if (g_hg_tune_fps_threads == 128 || g_hg_tune_fps_threads == 256) th = n <= 128 * 16 ? g_hg_tune_fps_threads : th;
   const int ppt = (n + th - 1) / th;
 #define HG_FPS_CASE(P, TH)                                                                                \
   if (th == TH && ppt <= P) {                                                                             \
@@ -648,6 +713,11 @@ int launch_fps(const float *dataset, int b, int n, int m, const long long *start
     HG_CHECK_LAUNCH("fps_kernel");                                                                        \
     return HG_OK;                                                                                         \
   }
+  HG_FPS_CASE(1, 128)
+  HG_FPS_CASE(2, 128)
+  HG_FPS_CASE(4, 128)
+  HG_FPS_CASE(8, 128)
+  HG_FPS_CASE(16, 128)
   HG_FPS_CASE(1, 256)
   HG_FPS_CASE(2, 256)
   HG_FPS_CASE(4, 256)

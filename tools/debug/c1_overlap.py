@@ -55,3 +55,35 @@ for temporal in (False, True):
         print(mode, "temporal" if temporal else "cold", "median ms %.4f" % np.median(ts[5:]), "loss", float(out))
 print("same grads:", torch.equal(res[("serial", False)][2], res[("overlap", False)][2]),
       torch.equal(res[("serial", True)][2], res[("overlap", True)][2]))
+
+# the two arms alone (graphs, L2 flushed): which one is the critical path
+def arm(which, temporal=False):
+    cd, hd, kd = ChamferDist(), HausdorffDist(), KNNDist(k=5).temporal_seeds(temporal)
+    def fn():
+        adv.grad.zero_()
+        with shared_distance_pass():
+            loss = kd(adv) if which == "knn" else cd(adv, ori) + hd(adv, ori)
+        loss.backward()
+        return loss
+    return fn
+
+for which, temporal in (("knn", False), ("knn", True), ("cd+hd", False)):
+    fn = arm(which, temporal)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            fn()
+    torch.cuda.current_stream().wait_stream(side)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        out = fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(30):
+        flush.zero_(); flush_rd.sum()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record(); g.replay(); e.record()
+        torch.cuda.synchronize()
+        ts.append(s.elapsed_time(e))
+    print("arm", which, "temporal" if temporal else "cold", "median ms %.4f" % np.median(ts[5:]))
