@@ -248,6 +248,275 @@ __global__ void __launch_bounds__(128) knn_tc_filter_kernel(const __grid_constan
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem) : "memory");
 }
 
+// ---- 1b. fused single pass: tensor-core filter + exact FP32 evaluation out of the SAME shared-memory tiles ----------
+// The candidate tile that TMA brought in for the MMA holds, row by row, exactly the FP32 features the reference
+// arithmetic needs.  So a column the TF32 distances cannot rule out is evaluated on the spot -- the thread (= query row)
+// keeps its own row in registers (C <= 64) or re-reads it from the A panels, walks the candidate's 128-byte-swizzled row
+// with conflict-free 16-byte loads, runs the reference's sequential FMA chain and inserts (value, index) into a sorted
+// register list of the row's KM smallest.  Columns are visited in ascending order, so a strict '<' insertion keeps the
+// lowest index among equal values (torch.topk's order on this path, hg_knn.cu).  The admission threshold starts from
+// the k-th smallest of 32 column-class minima of tile 0 (an upper bound on the k-th smallest approximate distance) and
+// follows the list's k-th EXACT value from then on:  approx_j <= (k-th exact so far) + 2 eps  is necessary for column j
+// to enter the final list, eps bounding |approximate - reference| for the row (header).  One pass over the tiles:
+// half the TMA traffic and MMAs of the two-pass filter, no candidate lists in global memory, no L2 gathers.
+template <int KM>
+struct TcList {
+  float v[KM];
+  int id[KM];
+  __device__ __forceinline__ void init() {
+#pragma unroll
+    for (int s = 0; s < KM; ++s) {
+      v[s] = CUDART_INF_F;
+      id[s] = 0;
+    }
+  }
+  // sorted insertion, strict '<': an equal value stays behind the entries already there
+  __device__ __forceinline__ void push(float d, int j) {
+#pragma unroll
+    for (int s = KM - 1; s >= 1; --s) {
+      const bool above = d < v[s - 1], here = d < v[s];
+      id[s] = above ? id[s - 1] : (here ? j : id[s]);
+      v[s] = above ? v[s - 1] : (here ? d : v[s]);
+    }
+    if (d < v[0]) {
+      v[0] = d;
+      id[0] = j;
+    }
+  }
+  // k1-th smallest = maximum of the first k1 entries of the ascending list (written as a masked maximum: a
+  // "select entry k1-1" chain is turned into a dynamically indexed load by the compiler, which sends the list to local memory)
+  __device__ __forceinline__ float kth(int k1) const {
+    float r = -CUDART_INF_F;
+#pragma unroll
+    for (int s = 0; s < KM; ++s)
+      if (s < k1) r = fmaxf(r, v[s]);
+    return r;
+  }
+};
+
+template <int C, int KM>
+__global__ void __launch_bounds__(128, C <= 64 ? 2 : 1)
+    knn_tc_fused_kernel(const __grid_constant__ CUtensorMap map, int K, int k1, int b0, const float *__restrict__ xx,
+                        const float *__restrict__ xxmax, float *__restrict__ vals, int *__restrict__ idx) {
+  constexpr int NP = C / kTcPanelK;
+  constexpr int kABytes = kTcRows * 128, kBBytes = kTcTile * 128;
+  constexpr bool kOwnInRegs = C <= 64;
+  extern __shared__ __align__(1024) unsigned char smraw[];
+  unsigned char *sA = smraw, *sB = smraw + NP * kABytes;
+  float *sxx = reinterpret_cast<float *>(sB + NP * kBBytes);
+  __shared__ __align__(8) uint64_t bar_a, bar_b, bar_mma;
+  __shared__ uint32_t tmem_base_s;
+
+  const int bl = blockIdx.y, b = b0 + bl, row0 = blockIdx.x * kTcRows;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int ntiles = (K + kTcTile - 1) / kTcTile;
+
+  if (tid == 0) {
+    hg_mbar_init(&bar_a, 1);
+    hg_mbar_init(&bar_b, 1);
+    hg_mbar_init(&bar_mma, 1);
+    hg_mbar_init_fence();
+  }
+  if (warp == 0) {
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(hg_smem_addr(&tmem_base_s))
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int j = tid; j < ntiles * kTcTile; j += 128) sxx[j] = j < K ? xx[(size_t)b * K + j] : CUDART_INF_F;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+
+  if (tid == 0) {
+    hg_mbar_expect_tx(&bar_a, NP * kABytes);
+    for (int p = 0; p < NP; ++p) tc_tma_load_3d(sA + p * kABytes, &map, &bar_a, p * kTcPanelK, row0, b);
+  }
+
+  const int i = row0 + tid;
+  const bool live = i < K;
+  const float xi = live ? sxx[i] : 0.f;
+  const float eps = 1.1f * 0.00390625f * sqrtf(xi * xxmax[b]) + 1e-5f * (xi + xxmax[b]);
+  const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+  const unsigned sw = (unsigned)(tid & 7);  // swizzle phase of this thread's own row in the A panels
+
+  float4 own[kOwnInRegs ? C / 4 : 1];
+  TcList<KM> top;
+  top.init();
+  float thr = CUDART_INF_F;
+  unsigned phase_b = 0, phase_m = 0;
+
+  // reference distances of columns jr0, jr1 of the current tile (two independent chains in flight): zz = sequential
+  // FMA chain over the channels in ascending order, dist = (xx_j + (-2 zz)) + xx_i; + 0.0f turns a -0.0 into +0.0 like
+  // the selection kernels do
+  auto exact2 = [&](int jr0, int jr1, float xxj0, float xxj1, float &d0, float &d1) {
+    float acc0 = 0.f, acc1 = 0.f;
+    const unsigned sw0 = (unsigned)(jr0 & 7), sw1 = (unsigned)(jr1 & 7);
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+      const unsigned char *r0 = sB + p * kBBytes + jr0 * 128, *r1 = sB + p * kBBytes + jr1 * 128;
+      const unsigned char *rowi = sA + p * kABytes + tid * 128;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const float4 v0 = *reinterpret_cast<const float4 *>(r0 + ((c ^ sw0) << 4));
+        const float4 v1 = *reinterpret_cast<const float4 *>(r1 + ((c ^ sw1) << 4));
+        const float4 a = kOwnInRegs ? own[kOwnInRegs ? p * 8 + c : 0]
+                                    : *reinterpret_cast<const float4 *>(rowi + ((c ^ sw) << 4));
+        acc0 = __fmaf_rn(a.x, v0.x, acc0);
+        acc1 = __fmaf_rn(a.x, v1.x, acc1);
+        acc0 = __fmaf_rn(a.y, v0.y, acc0);
+        acc1 = __fmaf_rn(a.y, v1.y, acc1);
+        acc0 = __fmaf_rn(a.z, v0.z, acc0);
+        acc1 = __fmaf_rn(a.z, v1.z, acc1);
+        acc0 = __fmaf_rn(a.w, v0.w, acc0);
+        acc1 = __fmaf_rn(a.w, v1.w, acc1);
+      }
+    }
+    d0 = __fadd_rn(__fadd_rn(__fadd_rn(xxj0, __fmul_rn(-2.0f, acc0)), xi), 0.0f);
+    d1 = __fadd_rn(__fadd_rn(__fadd_rn(xxj1, __fmul_rn(-2.0f, acc1)), xi), 0.0f);
+  };
+
+  for (int t = 0; t < ntiles; ++t) {
+    if (tid == 0) {
+      hg_mbar_expect_tx(&bar_b, NP * kBBytes);
+      for (int p = 0; p < NP; ++p) {
+        tc_tma_load_3d(sB + p * kBBytes, &map, &bar_b, p * kTcPanelK, t * kTcTile, b);
+        tc_tma_load_3d(sB + p * kBBytes + kABytes, &map, &bar_b, p * kTcPanelK, t * kTcTile + 128, b);
+      }
+      if (t == 0) tc_mbar_wait(&bar_a, 0);
+      tc_mbar_wait(&bar_b, phase_b);
+      tc_fence_after();
+      constexpr uint32_t idesc = tc_idesc(kTcRows, kTcTile);
+#pragma unroll
+      for (int p = 0; p < NP; ++p)
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          tc_mma_tf32(tmem, tc_smem_desc(sA + p * kABytes, ks * 32), tc_smem_desc(sB + p * kBBytes, ks * 32), idesc,
+                      (p | ks) ? 1u : 0u);
+      tc_commit(&bar_mma);
+    }
+    // every thread reads the tiles with ordinary loads below: each one observes the TMA completions itself
+    if (t == 0) {
+      tc_mbar_wait(&bar_a, 0);
+      if (kOwnInRegs) {
+#pragma unroll
+        for (int p = 0; p < NP; ++p)
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            own[kOwnInRegs ? p * 8 + c : 0] =
+                *reinterpret_cast<const float4 *>(sA + p * kABytes + tid * 128 + ((c ^ sw) << 4));
+      }
+    }
+    tc_mbar_wait(&bar_b, phase_b);
+    phase_b ^= 1;
+    tc_mbar_wait(&bar_mma, phase_m);
+    phase_m ^= 1;
+    __syncwarp();
+    tc_fence_after();
+
+    if (t == 0) {
+      // threshold for the first tile: k1-th smallest of the 32 column-class minima of its approximate distances
+      float m[32];
+#pragma unroll
+      for (int c = 0; c < 32; ++c) m[c] = CUDART_INF_F;
+#pragma unroll 1
+      for (int q = 0; q < kTcTile / 32; ++q) {
+        float acc[32];
+        tc_ld32(trow + (uint32_t)(q * 32), acc);
+        const float4 *sx4 = reinterpret_cast<const float4 *>(sxx + q * 32);
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4) {
+          const float4 xj = sx4[c4];
+          m[4 * c4] = fminf(m[4 * c4], fmaf(-2.0f, acc[4 * c4], xi + xj.x));
+          m[4 * c4 + 1] = fminf(m[4 * c4 + 1], fmaf(-2.0f, acc[4 * c4 + 1], xi + xj.y));
+          m[4 * c4 + 2] = fminf(m[4 * c4 + 2], fmaf(-2.0f, acc[4 * c4 + 2], xi + xj.z));
+          m[4 * c4 + 3] = fminf(m[4 * c4 + 3], fmaf(-2.0f, acc[4 * c4 + 3], xi + xj.w));
+        }
+      }
+#pragma unroll
+      for (int size = 2; size <= 32; size <<= 1)
+#pragma unroll
+        for (int stride = size >> 1; stride > 0; stride >>= 1)
+#pragma unroll
+          for (int a = 0; a < 32; ++a) {
+            const int p2 = a ^ stride;
+            if (p2 > a) {
+              const bool up = (a & size) == 0;
+              const float lo = fminf(m[a], m[p2]), hi = fmaxf(m[a], m[p2]);
+              m[a] = up ? lo : hi;
+              m[p2] = up ? hi : lo;
+            }
+          }
+      float tau = -CUDART_INF_F;  // m[k1 - 1] of the ascending array, as a masked maximum (see TcList::kth)
+#pragma unroll
+      for (int c = 0; c < 32; ++c)
+        if (c < k1) tau = fmaxf(tau, m[c]);
+      thr = tau + 2.0f * eps;
+    }
+
+    // the tile's 256-bit hit mask first, then every lane walks ITS hits (two per step) at its own pace: a warp takes
+    // max-over-lanes(hits in the tile) / 2 steps, not the sum over the eight 32-column chunks of the per-chunk maxima
+    unsigned hm[kTcTile / 32];
+#pragma unroll
+    for (int q = 0; q < kTcTile / 32; ++q) {
+      float acc[32];
+      tc_ld32(trow + (uint32_t)(q * 32), acc);
+      const float4 *sx4 = reinterpret_cast<const float4 *>(sxx + t * kTcTile + q * 32);
+      unsigned hits = 0u;
+#pragma unroll
+      for (int c4 = 0; c4 < 8; ++c4) {
+        const float4 xj = sx4[c4];
+        hits |= (fmaf(-2.0f, acc[4 * c4], xi + xj.x) <= thr ? 1u : 0u) << (4 * c4);
+        hits |= (fmaf(-2.0f, acc[4 * c4 + 1], xi + xj.y) <= thr ? 1u : 0u) << (4 * c4 + 1);
+        hits |= (fmaf(-2.0f, acc[4 * c4 + 2], xi + xj.z) <= thr ? 1u : 0u) << (4 * c4 + 2);
+        hits |= (fmaf(-2.0f, acc[4 * c4 + 3], xi + xj.w) <= thr ? 1u : 0u) << (4 * c4 + 3);
+      }
+      hm[q] = live ? hits : 0u;
+    }
+    auto next_hit = [&]() -> int {  // lowest set bit of the 256-bit mask, cleared; -1 when none is left
+      unsigned w = 0u;
+      int base = -1;
+#pragma unroll
+      for (int q = kTcTile / 32 - 1; q >= 0; --q)
+        if (hm[q]) {
+          w = hm[q];
+          base = q;
+        }
+#pragma unroll
+      for (int q = 0; q < kTcTile / 32; ++q)
+        if (q == base) hm[q] = w & (w - 1u);
+      return base < 0 ? -1 : base * 32 + __ffs(w) - 1;
+    };
+    while (true) {
+      const int jr0 = next_hit();
+      if (!__any_sync(0xffffffffu, jr0 >= 0)) break;
+      if (jr0 >= 0) {
+        const int jr1 = next_hit();
+        const int jrb = jr1 >= 0 ? jr1 : jr0;
+        float d0, d1;
+        exact2(jr0, jrb, sxx[t * kTcTile + jr0], sxx[t * kTcTile + jrb], d0, d1);
+        if (d0 < top.v[KM - 1]) top.push(d0, t * kTcTile + jr0);
+        if (jr1 >= 0 && d1 < top.v[KM - 1]) top.push(d1, t * kTcTile + jr1);
+      }
+    }
+    thr = fminf(thr, (k1 == KM ? top.v[KM - 1] : top.kth(k1)) + 2.0f * eps);
+    tc_fence_before();
+    __syncthreads();  // the accumulator and the B panels are free again
+    tc_fence_after();
+  }
+  if (live) {
+    const size_t o = ((size_t)b * K + i) * k1;
+#pragma unroll
+    for (int s = 0; s < KM; ++s)
+      if (s < k1) {
+        if (vals) vals[o + s] = top.v[s];
+        idx[o + s] = top.id[s];
+      }
+  }
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem) : "memory");
+}
+
 // ---- 2. exact re-evaluation + selection ---------------------------------------------------------------------------
 // reference distance (hg_knn.cu): zz = sequential FMA chain over the channels, dist = (xx_j + (-2 zz)) + xx_i
 template <int C>
@@ -460,6 +729,8 @@ int run_tc(const float *pc, const float *xx, float *xxmax, int B, int K, int k1,
   static HgPerDeviceOnce once;
   if (once.first()) {
     HG_CUDA(cudaFuncSetAttribute(knn_tc_filter_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    HG_CUDA((cudaFuncSetAttribute(knn_tc_fused_kernel<C, 20>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)));
+    HG_CUDA((cudaFuncSetAttribute(knn_tc_fused_kernel<C, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)));
     HG_CUDA(cudaFuncSetAttribute(knn_tc_exact_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
   }
   knn_tc_max_kernel<<<B, 256, 0, stream>>>(xx, K, xxmax);
@@ -476,6 +747,15 @@ int run_tc(const float *pc, const float *xx, float *xxmax, int B, int K, int k1,
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     HG_REQUIRE(cr == CUDA_SUCCESS, HG_E_UNSUPPORTED, "knn (tensor-core path): cuTensorMapEncodeTiled failed (%d)", (int)cr);
     dim3 grid((K + kTcRows - 1) / kTcRows, nb);
+    if (g_hg_tune_knn_tc_off != 3) {  // (3: the two-kernel filter + gather path, kept for A/B)
+      // vals / idx are indexed with the global cloud number inside the fused kernel
+      if (k1 <= 20)
+        knn_tc_fused_kernel<C, 20><<<grid, 128, fsmem, stream>>>(map, K, k1, b0, xx, xxmax, vals, idx);
+      else
+        knn_tc_fused_kernel<C, 32><<<grid, 128, fsmem, stream>>>(map, K, k1, b0, xx, xxmax, vals, idx);
+      HG_CHECK_LAUNCH("knn_tc_fused_kernel");
+      continue;
+    }
     knn_tc_filter_kernel<C><<<grid, 128, fsmem, stream>>>(map, K, k1, b0, xx, xxmax, cand, cnt);
     HG_CHECK_LAUNCH("knn_tc_filter_kernel");
     const int nrows = nb * K;
