@@ -191,8 +191,7 @@ __device__ __forceinline__ int hg_csr_next(const int *__restrict__ list, int p0,
 
 // ---- tensor-core kNN prefilter for feature clouds (hg_knn_tc.cu) ---------------------------------------------------
 bool hg_knn_tc_supported(int K, int C, int k1);
-int hg_knn_tc_run(const float *pc, const float *xx, int B, int K, int C, int k1, float *vals, int *idx, void *scratch,
-                  size_t scratch_bytes, cudaStream_t stream);
+int hg_knn_tc_run(const float *pc, const float *xx, int B, int K, int C, int k1, float *vals, int *idx, cudaStream_t stream);
 
 // ---- 3-D streaming kNN (hg_knn3.cu) ---------------------------------------------------------------------------
 #define HG_KNN_FORM_EXPANDED 0  // dist = (xx_j + (-2 zz)) + xx_i   (KNNDist / DGCNN)

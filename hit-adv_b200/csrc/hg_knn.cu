@@ -533,13 +533,14 @@ HG_API int hg_knn_self_temporal_f32(const float *pc, int B, int K, int C, int k1
   float *dist = (float *)((char *)workspace + hg_align((size_t)B * K * sizeof(float)));
   knn_sumsq_kernel<<<grid_for((long long)B * K, 256), 256, 0, stream>>>(pc, (long long)B * K, C, xx);
   HG_CHECK_LAUNCH("knn_sumsq_kernel");
-  // feature clouds of DGCNN's shapes: tensor-core prefilter + exact FP32 re-evaluation (hg_knn_tc.cu); everything else
-  // (and hg_tune("knn_tc", 1)) takes the FP32 distance tile + row select below
-  // (fewer CTAs than SMs -- small batches -- leave the serial TMA -> MMA -> read-back chain of a CTA exposed: measured
-  // 105 us against 95 us at 8 x 1024 x 64, so those stay on the FP32 path unless hg_tune("knn_tc", 2) forces it)
-  const bool tc_fills = (long long)B * ((K + 127) / 128) >= hg_sm_count() || g_hg_tune_knn_tc_off == 2;
+  // feature clouds of DGCNN's shapes: tensor-core filter fused with the exact FP32 evaluation (hg_knn_tc.cu); everything
+  // else (and hg_tune("knn_tc", 1)) takes the FP32 distance tile + row select below
+  // (small batches leave the serial chain of a CTA exposed -- measured at K = 1024, C = 64: 16 clouds 103 us against
+  // 144 us, 8 clouds 100 against 95, 4 clouds 96 against 65 -- so fewer CTAs than half the SMs stay on the FP32 path
+  // unless hg_tune("knn_tc", 2) forces the tensor-core kernel)
+  const bool tc_fills = 2LL * B * ((K + 127) / 128) >= hg_sm_count() || g_hg_tune_knn_tc_off == 2;
   if (g_hg_tune_knn_tc_off != 1 && tc_fills && hg_knn_tc_supported(K, C, k1) && (reinterpret_cast<uintptr_t>(pc) & 15) == 0)
-    return hg_knn_tc_run(pc, xx, B, K, C, k1, vals, idx, dist, need - hg_align((size_t)B * K * sizeof(float)), stream);
+    return hg_knn_tc_run(pc, xx, B, K, C, k1, vals, idx, stream);
   const size_t per = (size_t)K * K * sizeof(float);
   int nb = (int)(kGenericScratchBytes / per);
   if (nb < 1) nb = 1;

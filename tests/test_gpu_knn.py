@@ -213,18 +213,19 @@ def test_knn_outlier_backward_fused_and_general_paths_give_the_same_bits():
     assert grads[0].abs().max() > 0 and torch.equal(grads[0], grads[1])
 
 
-# ---- tensor-core prefilter (hg_knn_tc.cu): same values and indices as the FP32 path and the oracle --------------------
+# ---- tensor-core filter + exact evaluation (hg_knn_tc.cu): same values and indices as the FP32 path and the oracle --------------------
 @pytest.mark.parametrize("tc_off", [2, 1])
 @pytest.mark.parametrize("C,K,k1,kind", [(64, 1024, 20, "gauss"), (128, 512, 20, "gauss"), (32, 300, 7, "gauss"),
                                          (96, 777, 32, "gauss"), (64, 512, 20, "prototypes"), (64, 640, 5, "scaled"),
                                          (128, 1024, 20, "dups")])
 def test_knn_feature_clouds_tensor_core_vs_oracle(oracle, F, C, K, k1, kind, tc_off):
-    """DGCNN-shaped feature clouds (C a multiple of 32, 256 <= K <= 4096) take the tcgen05 TF32 prefilter + exact FP32
-    re-evaluation (`hg_tune("knn_tc", 2)` forces it for batches too small to fill the machine, as here);
+    """DGCNN-shaped feature clouds (C a multiple of 32, 256 <= K <= 4096) take the tcgen05 TF32 filter fused with the
+    exact FP32 evaluation (`hg_tune("knn_tc", 2)` forces it for batches too small to fill the machine, as here);
     `hg_tune("knn_tc", 1)` forces the FP32 tile + row-select path.  Both must give the oracle's values
-    and indices bit for bit -- including feature clouds made of a few prototypes (massive exact ties: the candidate
-    lists overflow and the rows are re-evaluated in full), widely different feature scales (the TF32 error bound is
-    per row) and duplicated points."""
+    and indices bit for bit -- including feature clouds made of a few prototypes (massive exact ties: every column is
+    a hit and is evaluated exactly), widely different feature scales (the TF32 error bound is per row), duplicated
+    points, a cloud size that is no multiple of the tile (K = 300, 777) and lists longer than the neighbour count
+    (k = 7 in a 20-slot list, 32 in 32)."""
     from hitgeom._lib import lib
 
     rng = np.random.default_rng(C + K)

@@ -21,9 +21,7 @@ $NCU --set full --import-source on -k regex:knn3_kernel -s 1 -c 1 -f -o gpurun_o
   python tools/prof_one.py knn 1024 16384 0 0 2 >> gpurun_out/r2_ncu.log 2>&1
 $NCU --set full --import-source on -k regex:nn_bidir_d3_kernel -s 2 -c 1 -f -o gpurun_out/r2_prof_nn_388x1024 \
   python tools/prof_one.py nn 388 1024 >> gpurun_out/r2_ncu.log 2>&1
-$NCU --set full --import-source on -k regex:knn_tc_filter -s 2 -c 1 -f -o gpurun_out/r2_prof_knn_tc_filter \
-  python tools/debug/prof_knn_tc.py 64 >> gpurun_out/r2_ncu.log 2>&1
-$NCU --set full --import-source on -k regex:knn_tc_exact -s 2 -c 1 -f -o gpurun_out/r2_prof_knn_tc_exact \
+$NCU --set full --import-source on -k regex:knn_tc_fused -s 2 -c 1 -f -o gpurun_out/r2_prof_knn_tc_fused \
   python tools/debug/prof_knn_tc.py 64 >> gpurun_out/r2_ncu.log 2>&1
 $NCU --set full --import-source on -k regex:scatter_bulk -s 2 -c 1 -f -o gpurun_out/r2_prof_scatter_bulk \
   python tools/debug/prof_scatter.py 64 >> gpurun_out/r2_ncu.log 2>&1
