@@ -431,10 +431,14 @@ def distance_record(workload, B, N, name, steps, warmup, rank, world, local, wit
     knn_ms, knn_n = _lib.prof_read("knn")
     _lib.prof_enable(False)
     clocks = sampler.stop() if sampler else {}
-    if small:  # (the pass above ran the one-stream order: its gradient sums the three terms in another order)
+    if small:
+        # the replays write into the gradient buffer that was current at capture time; the eager passes above replaced
+        # adv_d.grad (and the last one ran the one-stream order, which sums the three terms in another order)
         step()
         torch.cuda.synchronize()
-    grad_dev = adv_d.grad.detach().clone()
+        grad_dev = graph.hold[0].detach().clone()
+    else:
+        grad_dev = adv_d.grad.detach().clone()
 
     # ---- the same step with temporal kNN seeds (attack-loop usage: KNNDist.temporal_seeds) -----------------------
     temporal = None

@@ -50,9 +50,12 @@ int hg_device_info(int *sm_count, int *clock_khz, long long *l2_bytes, long long
 #define HG_PROF_GROUP 3    /* gather_channel_major_kernel (group_points / gather_points) */
 #define HG_PROF_NTAGS 4
 /* Development knobs for A/B measurements (not part of the stable ABI): "scatter" = 0 auto / 1 staged / 2 bulk-copy;
- * "knn_tc" = 1 switches the tensor-core kNN prefilter of feature clouds off, 2 forces it for small batches;
+ * "knn_tc" = 1 switches the tensor-core kNN kernel of feature clouds off, 2 forces it for small batches;
  * "nn_exact" = 0 runs the experimental 4-operation approximate tracker (+ exact recovery) in hg_nn_bidir_f32
- * instead of the default 5-operation exact tracker (same results; see hg_nn_bidir.cu for why it is not the default). */
+ * instead of the default 5-operation exact tracker (same results; see hg_nn_bidir.cu for why it is not the default);
+ * "small_fused" = 1 sends clouds that fit in shared memory down the general finish / kNN-backward kernels as well
+ * (same results; the tests run both); "knn_win" = Z-order window of the small-cloud kNN seeds (0 = default);
+ * "fps_threads" = 128 | 256 threads per cloud in furthest point sampling for clouds up to 2048 points (0 = default). */
 int hg_tune(const char *key, int value);
 unsigned long long hg_launch_count(void); /* kernels launched by this library since it was loaded */
 void hg_prof_enable(int on);

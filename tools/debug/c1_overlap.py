@@ -53,8 +53,12 @@ for temporal in (False, True):
             ts.append(s.elapsed_time(e))
         res[(mode, temporal)] = (np.median(ts[5:]), float(out), adv.grad.clone())
         print(mode, "temporal" if temporal else "cold", "median ms %.4f" % np.median(ts[5:]), "loss", float(out))
-print("same grads:", torch.equal(res[("serial", False)][2], res[("overlap", False)][2]),
+print("same grads serial-vs-overlap:", torch.equal(res[("serial", False)][2], res[("overlap", False)][2]),
       torch.equal(res[("serial", True)][2], res[("overlap", True)][2]))
+print("same grads cold-vs-temporal: serial", torch.equal(res[("serial", False)][2], res[("serial", True)][2]),
+      "overlap", torch.equal(res[("overlap", False)][2], res[("overlap", True)][2]))
+d = (res[("overlap", False)][2] - res[("overlap", True)][2]).abs()
+print("overlap cold-vs-temporal max abs diff", float(d.max()), "nonzero", int((d > 0).sum()))
 
 # the two arms alone (graphs, L2 flushed): which one is the critical path
 def arm(which, temporal=False):
