@@ -1,5 +1,5 @@
-// hg_knn_tc.cu -- tensor-core prefilter for the k-nearest-neighbour search on FEATURE clouds (DGCNN edge-conv layers
-// 2-4: C = 64, 64, 128 channels, model/dgcnn_cls.py:7-13), followed by an exact FP32 re-evaluation.
+// hg_knn_tc.cu -- k-nearest-neighbour search on FEATURE clouds (DGCNN edge-conv layers 2-4: C = 64, 64, 128 channels,
+// model/dgcnn_cls.py:7-13): a tensor-core filter fused with the exact FP32 evaluation of what it lets through.
 //
 // The distance matrix of a C-channel cloud is a real contraction (2*C FLOP per pair), the one place on this path where
 // the 5th-generation tensor cores are admissible -- provided every index stays the reference's.
@@ -12,12 +12,12 @@
 //   four warps read it back with tcgen05.ld (thread = row) and turn it into a hit mask: columns whose approximate
 //   distance is <= threshold + 2 eps, where eps bounds |approximate - reference| for that row: TF32 keeps 11 significant
 //   bits of each operand, so |zz_tf32 - zz| <= |x_i||x_j| 2^-9 and eps_i = 1.1 * 2^-8 |x_i| max|x| + (FP32 rounding of
-//   both sides).  Every hit is evaluated EXACTLY on the spot, out of the same shared-memory tile (section 1b below).
+//   both sides).  Every hit is evaluated EXACTLY on the spot, out of the same shared-memory tile (see the kernel's comment).
 // Nothing of size K x K is stored, and no candidate list leaves the SM.
 //
 // History (round 2): a two-kernel version -- two-pass filter writing candidate lists, then a warp-per-row exact kernel
 // gathering the candidates' rows from L2 -- took 163 us at 32 x 1024 x 64 (filter 50 us, gather-bound exact kernel 88 us);
-// the fused pass takes 135 us for the whole call.  A variant with two threads per row (16 warps per SM, two partial lists
+// the fused pass takes 131 us for the whole call (98 us the kernel).  A variant with two threads per row (16 warps per SM, two partial lists
 // merged at the end) was slower (156 us): the exact phase is bound by shared-memory bandwidth (random candidate rows:
 // 1.9 wavefronts per ideal one), not by latency, and two lists admit more candidates than one.
 #include <cuda.h>
@@ -100,7 +100,7 @@ __host__ __device__ constexpr uint32_t tc_idesc(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-// ---- 1b. fused single pass: tensor-core filter + exact FP32 evaluation out of the SAME shared-memory tiles ----------
+// ---- fused single pass: tensor-core filter + exact FP32 evaluation out of the SAME shared-memory tiles --------------
 // The candidate tile that TMA brought in for the MMA holds, row by row, exactly the FP32 features the reference
 // arithmetic needs.  So a column the TF32 distances cannot rule out is evaluated on the spot -- the thread (= query row)
 // keeps its own row in registers (C <= 64) or re-reads it from the A panels, walks the candidate's 128-byte-swizzled row
