@@ -145,6 +145,34 @@ __global__ void __launch_bounds__(128) query_ball_torch_kernel(int N, int S, flo
 }
 
 // index_points: out[b,e,:] = points[b, idx[b,e], :]
+// Two shapes matter (model/pointnet2_utils.py:110-138 sample_and_group): coordinate rows (C = 3: one thread per row,
+// the index read once, 32-bit arithmetic) and feature rows (C a multiple of 4: one 16-byte chunk per thread).  The
+// generic kernel does 64-bit divisions per ELEMENT, which cost more than the copy.
+template <int C>
+__global__ void __launch_bounds__(256) index_points_rows_kernel(const float *__restrict__ points,
+                                                                const long long *__restrict__ idx, int N, int M,
+                                                                unsigned rows, float *__restrict__ out) {
+  for (unsigned r = blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += gridDim.x * blockDim.x) {
+    const unsigned b = r / (unsigned)M;
+    const float *src = points + ((size_t)b * N + (size_t)idx[r]) * C;
+    float v[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) v[c] = __ldg(src + c);
+#pragma unroll
+    for (int c = 0; c < C; ++c) out[(size_t)r * C + c] = v[c];
+  }
+}
+
+__global__ void __launch_bounds__(256) index_points_vec4_kernel(const float *__restrict__ points,
+                                                                const long long *__restrict__ idx, int N, int M, int C4,
+                                                                unsigned chunks, float4 *__restrict__ out) {
+  for (unsigned g = blockIdx.x * blockDim.x + threadIdx.x; g < chunks; g += gridDim.x * blockDim.x) {
+    const unsigned r = g / (unsigned)C4, c4 = g - r * (unsigned)C4;
+    const unsigned b = r / (unsigned)M;
+    out[g] = __ldg(reinterpret_cast<const float4 *>(points + ((size_t)b * N + (size_t)idx[r]) * (4 * (size_t)C4)) + c4);
+  }
+}
+
 __global__ void __launch_bounds__(256) index_points_kernel(const float *__restrict__ points,
                                                            const long long *__restrict__ idx, int B, int N, int C,
                                                            int M, float *__restrict__ out) {
@@ -218,9 +246,18 @@ HG_API int hg_index_points_f32(const float *points, const int64_t *idx, int B, i
                                hgStream stream_) {
   HG_REQUIRE(points && idx && out, HG_E_BADARG, "index_points: null pointer");
   HG_REQUIRE(B > 0 && N > 0 && C > 0 && M > 0, HG_E_BADARG, "index_points: sizes must be positive");
-  const long long total = (long long)B * M * C;
-  index_points_kernel<<<grid_for(total, 256), 256, 0, hg_stream(stream_)>>>(points, (const long long *)idx, B, N, C, M,
-                                                                            out);
+  const long long total = (long long)B * M * C, rows = (long long)B * M;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(points) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+  if (C == 3 && rows < (1LL << 31)) {
+    index_points_rows_kernel<3><<<grid_for(rows, 256), 256, 0, hg_stream(stream_)>>>(points, (const long long *)idx, N, M,
+                                                                                    (unsigned)rows, out);
+  } else if ((C & 3) == 0 && aligned && total / 4 < (1LL << 31)) {
+    index_points_vec4_kernel<<<grid_for(total / 4, 256), 256, 0, hg_stream(stream_)>>>(
+        points, (const long long *)idx, N, M, C / 4, (unsigned)(total / 4), reinterpret_cast<float4 *>(out));
+  } else {
+    index_points_kernel<<<grid_for(total, 256), 256, 0, hg_stream(stream_)>>>(points, (const long long *)idx, B, N, C, M,
+                                                                              out);
+  }
   HG_CHECK_LAUNCH("index_points");
   return HG_OK;
 }

@@ -51,6 +51,21 @@ def test_seams_vs_oracle(oracle, B, N, S, npoint):
         assert np.array_equal(out.cpu().numpy(), oracle.query_ball_torch(r, ns, xyz, new_xyz))
 
 
+@pytest.mark.parametrize("C", [3, 5, 8, 64, 131])
+@pytest.mark.parametrize("shape", [(50,), (50, 9)])
+def test_index_points_equals_advanced_indexing(C, shape):
+    """model/pointnet2_utils.py:43-60: `points[batch_indices, idx, :]`, for the coordinate-row kernel (C = 3), the
+    16-byte-chunk kernel (C a multiple of 4) and the generic one."""
+    from hitgeom import model_seams as ms
+
+    rng = np.random.default_rng(C)
+    pts = torch.randn(4, 300, C, device="cuda")
+    idx = gpu(rng.integers(0, 300, (4,) + shape).astype(np.int64))
+    out = ms.index_points(pts, idx)
+    ref = pts[torch.arange(4, device="cuda").view(4, *([1] * len(shape))).expand_as(idx), idx, :]
+    assert out.shape == ref.shape and torch.equal(out, ref)
+
+
 def test_index_points_backward_is_deterministic_sum():
     from hitgeom import model_seams as ms
 
