@@ -1015,15 +1015,17 @@ HG_API int hg_nn_bidir_f32(const float *gts, const float *preds, int B, int N2, 
     HG_CHECK_LAUNCH("nn_eps_kernel");
   }
 
-  int T = g_force_T ? g_force_T : (N1 >= 2048 ? 16 : 8);
+  // columns per lane: 16 halves the row broadcasts per pair but needs 12-warp occupancy to pay (tools/debug/nn_sweep.py,
+  // B200: 8 wins by 6 % at 2048 points, 2 % at 4096, level at 8192, loses from there)
+  int T = g_force_T ? g_force_T : (N1 >= 8192 ? 16 : 8);
   // rows per CTA: amortise the per-CTA column load and result merge (measured: >= 128 rows is flat, 64 costs
-  // ~10%), but keep several waves of CTAs on the machine
+  // ~4-10 %, 32 more), but keep several waves of CTAs on the machine
   int RB = g_force_RB;
   if (!RB) {
     const int ncg_ = (N1 + 32 * T - 1) / (32 * T);
     const int wpc = (ncg_ >= 4 && ncg_ % 4 == 0) ? 4 : (ncg_ >= 2 ? 2 : 1);
     RB = 512;
-    while (RB > kColBatch) {
+    while (RB > 2 * kColBatch) {
       const long long ctas = (long long)B * ((N2 + RB - 1) / RB) * ((ncg_ + wpc - 1) / wpc);
       if (ctas * wpc >= (long long)hg_sm_count() * 12 * 4) break;  // >= 4 waves of 12 warps per SM
       RB >>= 1;
