@@ -972,6 +972,7 @@ int knn3_small_main(const float *pc, int B, int N, int k1, float *vals, int *idx
   int gp = g_force_gp ? g_force_gp : (N <= 1280 ? 1 : 2);
   if (N > 2048 && gp < 2) gp = 2;
   if (N > 4096 && gp < 4) gp = 4;
+  if (!g_force_gp && k1 > 6 && N > 3072) gp = 4;  // longer lists: 1001 against 1257 us at 64 x 4096, k+1 = 20
   int qt = g_force_qt ? g_force_qt : 2;
   if (k1 <= 6) {
     if (qt == 4) return launch_small_gp<4, 6>(gp, pc, B, N, k1, vals, idx, thr0, sbound, stream, idx_state);
@@ -1043,7 +1044,9 @@ int hg_knn3_self_seeded_i32(const float *pc, int B, int N, int k1, float *vals, 
     return launch_form<HG_KNN_FORM_EXPANDED, int>(pc, pc, B, N, N, k1, vals, idx, nullptr, nullptr, stream, idx_state);
   float *sb_slot = (float *)((char *)workspace + hg_align((size_t)B * N * sizeof(int)));  // `params`: [B] stride 8
   float *thr_slot = (float *)((char *)sb_slot + hg_align((size_t)B * 8 * sizeof(float)));  // `thr0`: [B,N]
-  const int small_max = g_small_max_n > 0 ? (g_small_max_n < 8192 ? g_small_max_n : 8192) : (g_small_max_n < 0 ? -1 : 2047);
+  // (tools/debug/knn_mid_sweep.py, B200, k+1 = 6: 2048 points 209 against 311 us streaming, 3000: 317 / 403, 4096: 444 / 458,
+  // 8192: 1237 / 688)
+  const int small_max = g_small_max_n > 0 ? (g_small_max_n < 8192 ? g_small_max_n : 8192) : (g_small_max_n < 0 ? -1 : 4096);
   if (N <= small_max)  // clouds that fit in shared memory: deferred-drain kernel
     return knn3_small_self(pc, B, N, k1, vals, idx, thr_slot, sb_slot, stream, idx_state, state_valid != 0);
   if (idx_state && state_valid) {  // temporal seeds instead of the grid pre-pass

@@ -70,7 +70,7 @@ void hg_knn_tune(int seed_min_n, int neighbourhood);
  * requested k makes the next kNN call fail with HG_E_UNSUPPORTED.  Process-global, not thread-safe. */
 void hg_knn_force_shape(int qt, int gp);
 /* Benchmark / test-only: largest cloud whose self-kNN takes the small-cloud path (whole cloud resident in shared
- * memory, drain deferred): 0 = default (2047 points), a negative value switches the path off, at most 8192. */
+ * memory, drain deferred): 0 = default (4096 points), a negative value switches the path off, at most 8192. */
 void hg_knn_tune_small(int small_max_n);
 
 /* ---------------------------------------------------------------------------------------------------------

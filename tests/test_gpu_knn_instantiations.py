@@ -29,6 +29,7 @@ def F():
 
     yield functional
     functional.force_knn_shape(0, 0)
+    functional.tune_knn_small(0)
 
 
 def _inputs(n):
@@ -42,20 +43,23 @@ def _inputs(n):
 QT_FOR_K = {6: (1, 2, 4), 5: (1, 2, 4), 1: (4,), 20: (1, 2), 12: (2,), 32: (1,), 21: (1,)}
 
 
-@pytest.mark.parametrize("n", [2048, 1024, 3000, 333])
+@pytest.mark.parametrize("n,path", [(2048, "streaming"), (3000, "streaming"), (2048, "small"), (1024, "small"),
+                                    (3000, "small"), (333, "small")])
 @pytest.mark.parametrize("gp", [1, 2, 4])
 @pytest.mark.parametrize("k1", sorted(QT_FOR_K))
-def test_self_knn_every_forced_instantiation(oracle, F, n, gp, k1):
-    """Self-kNN (KNNDist, DGCNN layer 1): n >= 2048 takes the grid-seeded streaming kernel (GP = 2 or 4; a forced 1
-    means 4 there), n < 2048 the small-cloud kernel (Z-order seeds, deferred drain; GP = 1, 2, 4); every QT the list
-    length admits."""
+def test_self_knn_every_forced_instantiation(oracle, F, n, path, gp, k1):
+    """Self-kNN (KNNDist, DGCNN layer 1).  Clouds up to 4096 points take the small-cloud kernel (Z-order seeds, deferred
+    drain; GP = 1, 2, 4), larger ones -- and these, with the small-cloud path switched off -- the grid-seeded streaming
+    kernel (GP = 2 or 4; a forced 1 means 4 there); every QT the list length admits."""
+    if path == "streaming":
+        F.tune_knn_small(-1)
     for tag, pc in _inputs(n):
         ov, oi = oracle.knn_self(pc, k1, threads=oracle.host_threads())
         for qt in QT_FOR_K[k1]:
             F.force_knn_shape(qt, gp)
             vals, idx = F.knn_self(gpu(pc), k1)
-            assert np.array_equal(vals.cpu().numpy(), ov), (tag, n, qt, gp, k1, "values")
-            assert np.array_equal(idx.cpu().numpy(), oi), (tag, n, qt, gp, k1, "indices")
+            assert np.array_equal(vals.cpu().numpy(), ov), (tag, n, path, qt, gp, k1, "values")
+            assert np.array_equal(idx.cpu().numpy(), oi), (tag, n, path, qt, gp, k1, "indices")
 
 
 def test_forced_shape_without_instantiation_fails_loudly(F):
@@ -101,11 +105,13 @@ def test_unseeded_expanded_form_every_forced_instantiation(oracle, F, gp, k1, qt
         assert np.array_equal(vals.cpu().numpy(), ov) and np.array_equal(idx.cpu().numpy(), oi), (qt, gp, k1)
 
 
-@pytest.mark.parametrize("B,n,k1", [(80, 2048, 6), (160, 2048, 20), (12, 16384, 6), (388, 1024, 6), (300, 1024, 20)])
+@pytest.mark.parametrize("B,n,k1", [(24, 8192, 6), (12, 8192, 20), (12, 16384, 6), (80, 2048, 6), (160, 2048, 20),
+                                    (388, 1024, 6), (300, 1024, 20)])
 def test_big_batch_variants_selected_naturally(oracle, F, B, n, k1):
-    """Batches large enough for launch_form to pick the big-batch instantiations by itself (no override): on a
-    148-SM part 80 x 2048 / k+1 = 6 and 12 x 16384 select <FOLD4, QT=4, KM=6, GP=4> -- the headline kernel of
-    bench.py's config-5 shard -- 160 x 2048 / k+1 = 20 selects <FOLD4, 2, 20, 4>, 388 x 1024 is config 1."""
+    """Batches large enough for the dispatch to pick the big-batch instantiations by itself (no override): on a
+    148-SM part 24 x 8192 / k+1 = 6 and 12 x 16384 select <FOLD4, QT=4, KM=6, GP=4> -- the headline kernel of
+    bench.py's config-5 shard -- 12 x 8192 / k+1 = 20 selects <FOLD4, 2, 20, 4>; up to 4096 points the small-cloud
+    kernel runs (388 x 1024 is config 1)."""
     F.force_knn_shape(0, 0)
     pc = jitter(clouds(B, n, 4242 + n, "surface" if B < 100 else "gauss"), 3)
     pc[0, : n // 8] = pc[0, n // 8 : 2 * (n // 8)]
@@ -116,7 +122,7 @@ def test_big_batch_variants_selected_naturally(oracle, F, B, n, k1):
 
 
 # ---- temporal seeds (hg_knn_self_temporal_f32): results never depend on the state ------------------------------------
-@pytest.mark.parametrize("n,k1", [(1024, 6), (700, 20), (2048, 6), (3000, 17), (40, 32)])
+@pytest.mark.parametrize("n,k1", [(1024, 6), (700, 20), (2048, 6), (3000, 17), (40, 32), (5000, 6), (4500, 20)])
 def test_temporal_seeds_never_change_results(oracle, F, n, k1):
     """State from a previous call on a nearby cloud, stale state, and garbage state (out of range, repeated entries,
     all zeros): values and indices are the oracle's bit for bit, and the state ends up holding this call's indices."""
