@@ -351,6 +351,10 @@ def distance_record(workload, B, N, name, steps, warmup, rank, world, local, wit
     if small:
         # config 1 is ~0.3 ms of kernel work behind ~25 launches: launch-bound.  An attack loop replays the step as a
         # CUDA graph (hitgeom.cw_knn graph=True); time that, and report the eager figure next to it.
+        # a fresh leaf (same storage) for the captured steps: its gradient accumulator is then created on the warm-up
+        # side stream, not on the legacy default stream the eager warm-up above ran on (PyTorch's rule for capturing a
+        # backward pass; the closures below see the rebinding)
+        adv_d = adv_d.detach().requires_grad_()
         adv_d.grad = torch.zeros_like(adv_d)
 
         def capture(fn):

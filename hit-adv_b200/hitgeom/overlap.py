@@ -11,7 +11,9 @@ low-occupancy tail, the distance pass is 2.6 CTAs per SM.  Launched on two strea
     loss.backward()                      # autograd runs each backward node on its forward stream: overlapped again
 
 Works eagerly and under CUDA-graph capture (the fork and the join are event dependencies of the capturing stream, so
-the branch is captured as a parallel arm of the graph).  Results are the same bits as the serial order: every kernel
+the branch is captured as a parallel arm of the graph).  PyTorch's rule for capturing a backward pass applies: the leaf
+tensors must have run their first backward on the warm-up side stream, not on the legacy default stream (create them,
+or re-create them with `.detach().requires_grad_()`, inside the warm-up stream context; tests/test_gpu_overlap.py).  Results are the same bits as the serial order: every kernel
 is deterministic and the terms are combined in the same expression.
 """
 import torch

@@ -51,14 +51,18 @@ def test_side_branch_eager_matches_serial():
 @pytest.mark.parametrize("temporal", [False, True])
 def test_side_branch_is_captured_as_a_parallel_arm_of_a_cuda_graph(temporal):
     ori = torch.from_numpy(clouds(64, 1024, 9)).cuda()
-    adv = torch.from_numpy(jitter(clouds(64, 1024, 9), 10)).cuda().requires_grad_()
-    adv.grad = torch.zeros_like(adv)
-    l0 = float(_step(adv, ori, False)())  # (a float: holding the loss tensor would keep this stream's autograd nodes alive)
-    g0 = adv.grad.clone()
-    fn = _step(adv, ori, True, temporal)
+    adv0 = torch.from_numpy(jitter(clouds(64, 1024, 9), 10)).cuda().requires_grad_()
+    adv0.grad = torch.zeros_like(adv0)
+    l0 = float(_step(adv0, ori, False)())
+    g0 = adv0.grad.clone()
+    # a fresh leaf for the graph: its gradient accumulator must be born on the warm-up stream, not on the legacy
+    # default stream the eager step above ran on (PyTorch's rule for capturing a backward pass)
+    adv = adv0.detach().clone().requires_grad_()
     side = torch.cuda.Stream()
     side.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(side):
+        adv.grad = torch.zeros_like(adv)
+        fn = _step(adv, ori, True, temporal)
         for _ in range(3):
             fn()
     torch.cuda.current_stream().wait_stream(side)
