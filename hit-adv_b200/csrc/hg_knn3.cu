@@ -974,6 +974,9 @@ int knn3_small_main(const float *pc, int B, int N, int k1, float *vals, int *idx
   if (N > 4096 && gp < 4) gp = 4;
   if (!g_force_gp && k1 > 6 && N > 3072) gp = 4;  // longer lists: 1001 against 1257 us at 64 x 4096, k+1 = 20
   int qt = g_force_qt ? g_force_qt : 2;
+  // small batches: one query per lane doubles the CTAs (32 x 1024, k+1 = 6: 51 against 65 us; tools/debug/knn_small_shapes.py)
+  // (short candidate lists only: at 16 x 4096 two queries per lane still win, 176 against 212 us)
+  if (!g_force_qt && N <= 1536 && (long long)B * ((N + 2 * kThreads - 1) / (2 * kThreads)) < 2LL * hg_sm_count()) qt = 1;
   if (k1 <= 6) {
     if (qt == 4) return launch_small_gp<4, 6>(gp, pc, B, N, k1, vals, idx, thr0, sbound, stream, idx_state);
     if (qt == 2) return launch_small_gp<2, 6>(gp, pc, B, N, k1, vals, idx, thr0, sbound, stream, idx_state);
