@@ -639,7 +639,9 @@ int launch_form(const float *q, const float *r, int B, int Nq, int Nr, int k1, f
     return HG_E_UNSUPPORTED;
   }
   if (k1 <= 6) {
-    if (!short_list && Nq >= 3 * kThreads && ctas(4) >= want)
+    // (four queries per lane need twice the CTAs to pay: 32 x 8192: 654 us with two against 695, 16 x 16384: 1080 / 1128;
+    // 64 x 8192 and up: four win -- tools/debug/knn_small_shapes.py big)
+    if (!short_list && Nq >= 3 * kThreads && ctas(4) >= 2 * want)
       return launch_qt<FORM, 4, 6, IdxT>(q, r, B, Nq, Nr, k1, vals, idx, thr0, sbound, stream, idx_state);
     if (Nq > kThreads && ctas(2) >= want)
       return launch_qt<FORM, 2, 6, IdxT>(q, r, B, Nq, Nr, k1, vals, idx, thr0, sbound, stream, idx_state);

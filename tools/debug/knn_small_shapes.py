@@ -10,7 +10,10 @@ from bench_ops import timeit
 from hitgeom.pointnet2_ops import _ext
 
 flush = (torch.empty(256 << 20, dtype=torch.uint8, device="cuda"), torch.zeros(64 << 20, dtype=torch.float32, device="cuda"))
-for B, N, k1 in ((32, 1024, 20), (32, 1024, 6), (388, 1024, 6), (388, 1024, 20), (64, 2048, 6), (32, 2048, 20), (16, 4096, 6)):
+SHAPES = ((32, 1024, 20), (32, 1024, 6), (388, 1024, 6), (388, 1024, 20), (64, 2048, 6), (32, 2048, 20), (16, 4096, 6))
+if len(sys.argv) > 1 and sys.argv[1] == 'big':
+    SHAPES = ((32, 8192, 6), (64, 8192, 6), (16, 16384, 6), (128, 16384, 6), (32, 8192, 20), (16, 16384, 20))
+for B, N, k1 in SHAPES:
     x = torch.from_numpy(make_clouds(B, N, 3)[1]).cuda()
     F.force_knn_shape(0, 0)
     ref = F.knn_self(x, k1)
