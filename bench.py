@@ -545,9 +545,15 @@ def distance_record(workload, B, N, name, steps, warmup, rank, world, local, wit
                          "frac": tf / fp32_peak_tflops if fp32_peak_tflops else None,
                          "share_of_step": avg * (t_n / max(steps, 1)) / ms_local if ms_local > 0 else None}
     step_tflops = pairs_step * FLOP_PER_PAIR / (ms_local * 1e-3) / 1e12
+    try:  # measured FFMA throughput next to the computed figure (synchronising probe, outside every timed region)
+        fp32_measured = _lib.probe_fp32_peak()
+    except Exception:  # noqa: BLE001
+        fp32_measured = None
     roofline = {
         "bound": "fp32", "kernel": kname, "achieved": achieved, "peak": fp32_peak_tflops, "unit": "TFLOP/s",
         "frac": achieved / fp32_peak_tflops if fp32_peak_tflops else None,
+        "peak_measured": fp32_measured, "frac_of_measured_peak": achieved / fp32_measured if fp32_measured else None,
+        "peak_measured_source": "hg_probe_fp32_peak: 16 independent FFMA chains per thread, 8 CTAs of 256 threads per SM, CUDA events",
         "traffic": (tt.get(kname) or {}).get("dram_bytes"), "traffic_source": (tt.get(kname) or {}).get("source"),
         "peak_source": f"computed {info['sm_count']} SMs x 128 FP32 lanes x 2 x {sm_max_mhz:.0f} MHz (no FP32 figure in MEASURED_PEAKS.json)",
         "avg_launch_ms": k_avg_ms, "launches_timed": k_n, "algorithmic_pair_evals_per_launch": k_pairs,

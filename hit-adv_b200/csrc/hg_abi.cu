@@ -92,6 +92,51 @@ HG_API int hg_device_info(int *sm_count, int *clock_khz, long long *l2_bytes, lo
   return HG_OK;
 }
 
+// ---- FP32 peak probe (bench.py's roofline denominator, next to the computed figure) ----------------------------------
+// MEASURED_PEAKS.json carries no FP32 number, so the bench measures one: sixteen independent FFMA chains per thread
+// (no memory traffic, full occupancy), 2 FLOP per FFMA, CUDA events around the launch.  Synchronises: call it outside
+// timed regions.
+namespace {
+__global__ void __launch_bounds__(256) fp32_peak_kernel(float *__restrict__ out, int iters, float a, float b) {
+  float v[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = (float)(threadIdx.x + i);
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __fmaf_rn(v[i], a, b);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += v[i];
+  if (s == 12345.678f) out[0] = s;  // (keeps the chains alive; never true in practice)
+}
+}  // namespace
+
+HG_API int hg_probe_fp32_peak(float *tflops, float *scratch /*device, >= 4 bytes*/, hgStream stream_) {
+  cudaStream_t stream = hg_stream(stream_);
+  HG_REQUIRE(tflops && scratch, HG_E_BADARG, "probe_fp32_peak: null pointer");
+  const int iters = 8192, ctas = hg_sm_count() * 8;
+  cudaEvent_t e0, e1;
+  HG_CUDA(cudaEventCreate(&e0));
+  HG_CUDA(cudaEventCreate(&e1));
+  float best = 0.f;
+  for (int rep = 0; rep < 4; ++rep) {  // the first launch warms the clocks up
+    HG_CUDA(cudaEventRecord(e0, stream));
+    fp32_peak_kernel<<<ctas, 256, 0, stream>>>(scratch, iters, 1.0000001f, 1e-9f);
+    HG_CUDA(cudaEventRecord(e1, stream));
+    HG_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    HG_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    const double flop = 2.0 * 16.0 * iters * 256.0 * ctas;
+    if (rep > 0 && ms > 0.f) best = fmaxf(best, (float)(flop / (ms * 1e-3) / 1e12));
+  }
+  HG_CUDA(cudaEventDestroy(e0));
+  HG_CUDA(cudaEventDestroy(e1));
+  HG_CHECK_LAUNCH("fp32_peak_kernel");
+  *tflops = best;
+  return HG_OK;
+}
+
 // ---- optional per-kernel device timing (bench.py's roofline object) ---------------------------------------
 // When enabled, the launch of each tagged hot kernel is bracketed by CUDA events recorded on the launching
 // stream; hg_prof_read() returns the summed device time and the launch count.  Off by default (no events).

@@ -19,6 +19,7 @@ P, I, F, Z = _c_void_p, _c_int, _c_float, _c_size_t
 _SIGNATURES = {
     "hg_version": (I, []),
     "hg_last_error": (ctypes.c_char_p, []),
+    "hg_probe_fp32_peak": (I, [ctypes.POINTER(ctypes.c_float), P, P]),
     "hg_device_info": (I, [ctypes.POINTER(I), ctypes.POINTER(I), ctypes.POINTER(ctypes.c_longlong),
                            ctypes.POINTER(ctypes.c_longlong)]),
     "hg_nn_bidir_workspace_bytes": (Z, [I, I, I, I]),
@@ -155,6 +156,15 @@ def prof_read(tag):
 
 def launch_count():
     return int(lib().hg_launch_count())
+
+
+def probe_fp32_peak():
+    """Measured FP32 FFMA throughput of the current device [TFLOP/s] (hg_probe_fp32_peak)."""
+    out = _c_float()
+    scratch = torch.zeros(4, dtype=torch.float32, device="cuda")
+    check(lib().hg_probe_fp32_peak(ctypes.byref(out), scratch.data_ptr(), torch.cuda.current_stream().cuda_stream),
+          "hg_probe_fp32_peak")
+    return float(out.value)
 
 
 def device_info():

@@ -40,6 +40,9 @@ int hg_version(void);
 const char *hg_last_error(void);
 /* SM count, max SM clock [kHz], L2 bytes, global memory bytes of the current device. */
 int hg_device_info(int *sm_count, int *clock_khz, long long *l2_bytes, long long *mem_bytes);
+/* Measured FP32 FFMA throughput of the current device [TFLOP/s] (independent FFMA chains, no memory traffic): the roofline
+ * denominator bench.py reports next to the computed SMs x 128 x 2 x clock figure.  Synchronises the stream. */
+int hg_probe_fp32_peak(float *tflops, float *device_scratch, hgStream stream);
 
 /* Optional device timing of the hot kernels (used by bench.py for the roofline line).  hg_prof_enable(1) resets
  * the counters and brackets every launch of a tagged kernel with CUDA events on the launching stream;
