@@ -351,6 +351,14 @@ def distance_record(workload, B, N, name, steps, warmup, rank, world, local, wit
     if small:
         # config 1 is ~0.3 ms of kernel work behind ~25 launches: launch-bound.  An attack loop replays the step as a
         # CUDA graph (hitgeom.cw_knn graph=True); time that, and report the eager figure next to it.
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for s_, e_ in evs:  # the eager figure first (launch by launch, same streams): informational only
+            l2_flush()
+            s_.record()
+            fwd_bwd()
+            e_.record()
+        torch.cuda.synchronize()
+        eager_ms = sorted(s_.elapsed_time(e_) for s_, e_ in evs)[len(evs) // 2]
         # a fresh leaf (same storage) for the captured steps: its gradient accumulator is then created on the warm-up
         # side stream, not on the legacy default stream the eager warm-up above ran on (PyTorch's rule for capturing a
         # backward pass; the closures below see the rebinding)
@@ -384,17 +392,6 @@ def distance_record(workload, B, N, name, steps, warmup, rank, world, local, wit
         torch.cuda.synchronize()
         serial_ms = sum(s_.elapsed_time(e_) for s_, e_ in evs) / len(evs)
         del graph_serial
-        for _ in range(3):  # (the capture left the caching allocator in a new state: warm the eager path again)
-            fwd_bwd()
-        torch.cuda.synchronize()
-        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-        for s_, e_ in evs:
-            l2_flush()
-            s_.record()
-            fwd_bwd()
-            e_.record()
-        torch.cuda.synchronize()
-        eager_ms = sorted(s_.elapsed_time(e_) for s_, e_ in evs)[len(evs) // 2]  # median: informational only
 
         def step():
             graph.replay()

@@ -1,6 +1,7 @@
 // hg_common.cuh -- shared helpers of libhitgeom (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <math_constants.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -23,6 +24,16 @@ void hg_set_error(const char *fmt, ...);
       return (code);                  \
     }                                 \
   } while (0)
+
+// NVTX range around every compute entry point of the C ABI (header-only NVTX v3: a no-op unless a tool is attached),
+// so that nsys / ncu timelines of a reference run show which reference call a kernel belongs to
+struct HgNvtxRange {
+  explicit HgNvtxRange(const char *name) { nvtxRangePushA(name); }
+  ~HgNvtxRange() { nvtxRangePop(); }
+  HgNvtxRange(const HgNvtxRange &) = delete;
+  HgNvtxRange &operator=(const HgNvtxRange &) = delete;
+};
+#define HG_NVTX_RANGE(name) HgNvtxRange hg_nvtx_range_(name)
 
 extern int g_hg_tune_knn_win;     // hg_tune("knn_win", n)
 extern int g_hg_tune_knn_tc_off;  // hg_tune("knn_tc", 1) switches the tensor-core kNN prefilter off

@@ -176,6 +176,7 @@ __global__ void __launch_bounds__(kGradThreads) edge_feature_grad_kernel(const f
 // dgcnn_cls.py:16-43 (feature build only; the neighbour search is hg_knn_self_f32 / model_seams.knn)
 HG_API int hg_edge_feature_f32(const float *x, const int64_t *idx, int B, int C, int N, int k, float *out,
                                hgStream stream_) {
+  HG_NVTX_RANGE("hg_edge_feature_f32");
   cudaStream_t stream = hg_stream(stream_);
   HG_REQUIRE(x && idx && out, HG_E_BADARG, "edge_feature: null pointer");
   HG_REQUIRE(B > 0 && C > 0 && N > 0 && k > 0, HG_E_BADARG, "edge_feature: sizes must be positive");
@@ -215,6 +216,7 @@ HG_API size_t hg_edge_feature_grad_workspace_bytes(int B, int N, int k) {
 
 HG_API int hg_edge_feature_grad_f32(const float *grad_out, const int64_t *idx, int B, int C, int N, int k,
                                     float *grad_x, void *workspace, size_t workspace_bytes, hgStream stream_) {
+  HG_NVTX_RANGE("hg_edge_feature_grad_f32");
   cudaStream_t stream = hg_stream(stream_);
   HG_REQUIRE(grad_out && idx && grad_x, HG_E_BADARG, "edge_feature_grad: null pointer");
   HG_REQUIRE(B > 0 && C > 0 && N > 0 && k > 0, HG_E_BADARG, "edge_feature_grad: sizes must be positive");

@@ -147,6 +147,7 @@ __global__ void __launch_bounds__(kDefThreads) deform_bwd_kernel(
 
 HG_API int hg_hitadv_deform_fwd_f32(const float *ori, const float *centers, const float *perturb, const float *delta,
                                     int B, int K, int J, float *out, float *deno, hgStream stream_) {
+  HG_NVTX_RANGE("hg_hitadv_deform_fwd_f32");
   HG_REQUIRE(ori && centers && perturb && delta && out && deno, HG_E_BADARG, "hitadv_deform_fwd: null pointer");
   HG_REQUIRE(B > 0 && K > 0 && J > 0, HG_E_BADARG, "hitadv_deform_fwd: sizes must be positive");
   HG_REQUIRE(B <= 65535 && (size_t)J * 32 <= 160 * 1024, HG_E_UNSUPPORTED, "hitadv_deform_fwd: B or J too large");
@@ -162,6 +163,7 @@ HG_API int hg_hitadv_deform_fwd_f32(const float *ori, const float *centers, cons
 HG_API int hg_hitadv_deform_bwd_f32(const float *ori, const float *centers, const float *perturb, const float *delta,
                                     const float *out, const float *deno, const float *grad_out, int B, int K, int J,
                                     float *grad_perturb, float *grad_delta, hgStream stream_) {
+  HG_NVTX_RANGE("hg_hitadv_deform_bwd_f32");
   HG_REQUIRE(ori && centers && perturb && delta && out && deno && grad_out && grad_perturb && grad_delta, HG_E_BADARG,
              "hitadv_deform_bwd: null pointer");
   HG_REQUIRE(B > 0 && K > 0 && J > 0, HG_E_BADARG, "hitadv_deform_bwd: sizes must be positive");

@@ -149,6 +149,7 @@ HG_API int hg_chamfer_knn_step_host_f32(hgHostStep *s, const float *adv_h, const
                                         int chamfer_method, int knn_k, float knn_alpha, float chamfer_weight,
                                         float knn_weight, const float *weights_h, float *loss_h,
                                         float *cloud_loss_h, float *grad_adv_h) {
+  HG_NVTX_RANGE("hg_chamfer_knn_step_host_f32");
   HG_REQUIRE(s && adv_h && ori_h && loss_h && cloud_loss_h && grad_adv_h, HG_E_BADARG, "chamfer_knn_step_host: null pointer");
   HG_REQUIRE(B > 0, HG_E_BADARG, "chamfer_knn_step_host: B must be positive");
   HG_REQUIRE(chamfer_method >= 0 && chamfer_method <= 2, HG_E_BADARG, "chamfer_knn_step_host: method must be 0, 1 or 2");

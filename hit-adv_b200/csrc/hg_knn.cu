@@ -512,11 +512,13 @@ HG_API size_t hg_knn_self_workspace_bytes(int B, int K, int C, int k1) {
 
 HG_API int hg_knn_self_f32(const float *pc, int B, int K, int C, int k1, float *vals, int *idx, void *workspace,
                            size_t workspace_bytes, hgStream stream_) {
+  HG_NVTX_RANGE("hg_knn_self_f32");
   return hg_knn_self_temporal_f32(pc, B, K, C, k1, vals, idx, nullptr, 0, workspace, workspace_bytes, stream_);
 }
 
 HG_API int hg_knn_self_temporal_f32(const float *pc, int B, int K, int C, int k1, float *vals, int *idx, int *idx_state,
                                     int state_valid, void *workspace, size_t workspace_bytes, hgStream stream_) {
+  HG_NVTX_RANGE("hg_knn_self_temporal_f32");
   cudaStream_t stream = hg_stream(stream_);
   HG_REQUIRE(pc && idx, HG_E_BADARG, "knn_self: null pointer");
   HG_REQUIRE(B > 0 && K > 0 && C > 0, HG_E_BADARG, "knn_self: sizes must be positive");
@@ -562,6 +564,7 @@ HG_API int hg_knn_self_temporal_f32(const float *pc, int B, int K, int C, int k1
 
 HG_API int hg_knn_points_f32(const float *p1, const float *p2, int B, int N, int M, int K, float *dists, int64_t *idx,
                              hgStream stream_) {
+  HG_NVTX_RANGE("hg_knn_points_f32");
   HG_REQUIRE(p1 && p2 && idx, HG_E_BADARG, "knn_points: null pointer");
   HG_REQUIRE(B > 0 && N > 0 && M > 0, HG_E_BADARG, "knn_points: sizes must be positive");
   HG_REQUIRE(K >= 1 && K <= 64 && K <= M, HG_E_BADARG, "knn_points: need 1 <= K <= min(64, M); got K=%d M=%d", K, M);
@@ -571,6 +574,7 @@ HG_API int hg_knn_points_f32(const float *p1, const float *p2, int B, int N, int
 
 HG_API int hg_knn_outlier_fwd_f32(const float *vals, int B, int K, int k1, float alpha, const float *weights,
                                   float *value, float *mask, float *loss, hgStream stream_) {
+  HG_NVTX_RANGE("hg_knn_outlier_fwd_f32");
   HG_REQUIRE(vals && value && mask && loss, HG_E_BADARG, "knn_outlier_fwd: null pointer");
   HG_REQUIRE(B > 0 && K > 1 && k1 >= 2, HG_E_BADARG, "knn_outlier_fwd: need K > 1 and k >= 1");
   knn_outlier_fwd_kernel<<<B, 256, 0, hg_stream(stream_)>>>(vals, K, k1, alpha, weights, value, mask, loss);
@@ -586,6 +590,7 @@ HG_API size_t hg_knn_outlier_bwd_workspace_bytes(int B, int K, int k1) {
 HG_API int hg_knn_outlier_bwd_f32(const float *pc, const int *idx, const float *mask, const float *g, int B, int K,
                                   int C, int k1, float *grad_pc, void *workspace, size_t workspace_bytes,
                                   hgStream stream_) {
+  HG_NVTX_RANGE("hg_knn_outlier_bwd_f32");
   cudaStream_t stream = hg_stream(stream_);
   HG_REQUIRE(pc && idx && mask && g && grad_pc, HG_E_BADARG, "knn_outlier_bwd: null pointer");
   HG_REQUIRE(B > 0 && K > 1 && C > 0 && k1 >= 2, HG_E_BADARG, "knn_outlier_bwd: bad sizes");

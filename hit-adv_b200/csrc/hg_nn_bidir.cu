@@ -968,6 +968,7 @@ HG_API size_t hg_nn_bidir_workspace_bytes(int B, int N2, int N1, int D) {
 
 HG_API int hg_nn_bidir_f32(const float *gts, const float *preds, int B, int N2, int N1, int D, float *min1, int *arg1,
                            float *min2, int *arg2, void *workspace, size_t workspace_bytes, hgStream stream_) {
+  HG_NVTX_RANGE("hg_nn_bidir_f32");
   cudaStream_t stream = hg_stream(stream_);
   HG_REQUIRE(gts && preds && min1 && arg1 && min2 && arg2, HG_E_BADARG, "nn_bidir: null pointer");
   HG_REQUIRE(B > 0 && N1 > 0 && N2 > 0 && D > 0, HG_E_BADARG, "nn_bidir: sizes must be positive (B=%d N2=%d N1=%d D=%d)",
@@ -1072,6 +1073,7 @@ HG_API int hg_nn_bidir_f32(const float *gts, const float *preds, int B, int N2, 
 
 HG_API int hg_pairwise_dist_f32(const float *x, const float *y, int B, int Nx, int Ny, int D, float *P,
                                 hgStream stream_) {
+  HG_NVTX_RANGE("hg_pairwise_dist_f32");
   HG_REQUIRE(x && y && P, HG_E_BADARG, "pairwise_dist: null pointer");
   HG_REQUIRE(B > 0 && Nx > 0 && Ny > 0 && D > 0, HG_E_BADARG, "pairwise_dist: sizes must be positive");
   const long long total = (long long)B * Nx * Ny;
@@ -1082,6 +1084,7 @@ HG_API int hg_pairwise_dist_f32(const float *x, const float *y, int B, int Nx, i
 
 HG_API int hg_set_loss_f32(const float *min1, const float *min2, int B, int N1, int N2, int mode, float *loss1,
                            float *loss2, int *hd_arg1, int *hd_arg2, hgStream stream_) {
+  HG_NVTX_RANGE("hg_set_loss_f32");
   HG_REQUIRE(min1 && min2 && loss1 && loss2, HG_E_BADARG, "set_loss: null pointer");
   HG_REQUIRE(B > 0 && N1 > 0 && N2 > 0, HG_E_BADARG, "set_loss: sizes must be positive");
   HG_REQUIRE(mode == HG_MODE_CHAMFER || mode == HG_MODE_HAUSDORFF, HG_E_BADARG, "set_loss: bad mode %d", mode);
@@ -1100,6 +1103,7 @@ HG_API int hg_set_loss_bwd_f32(const float *gts, const float *preds, const int *
                                const int *hd_arg1, const int *hd_arg2, const float *g1, const float *g2, int B, int N2,
                                int N1, int D, int mode, float *grad_preds, float *grad_gts, void *workspace,
                                size_t workspace_bytes, hgStream stream_) {
+  HG_NVTX_RANGE("hg_set_loss_bwd_f32");
   cudaStream_t stream = hg_stream(stream_);
   HG_REQUIRE(gts && preds && arg1 && arg2 && grad_preds, HG_E_BADARG, "set_loss_bwd: null pointer");
   HG_REQUIRE(g1 || g2, HG_E_BADARG, "set_loss_bwd: g1 and g2 are both null (nothing to differentiate)");

@@ -737,6 +737,7 @@ int launch_fps(const float *dataset, int b, int n, int m, const long long *start
 // ================================================ C ABI =====================================================
 HG_API int hg_p2_gather_points(int b, int c, int n, int npoints, const float *points, const int *idx, float *out,
                                hgStream stream_) {
+  HG_NVTX_RANGE("hg_p2_gather_points");
   HG_REQUIRE(points && idx && out, HG_E_BADARG, "gather_points: null pointer");
   HG_REQUIRE(b > 0 && c > 0 && n > 0 && npoints > 0, HG_E_BADARG, "gather_points: sizes must be positive");
   return launch_gather(points, idx, b, c, n, npoints, out, hg_stream(stream_), -1);
@@ -749,6 +750,7 @@ HG_API size_t hg_p2_scatter_workspace_bytes(int b, int n, int nedges) {
 
 HG_API int hg_p2_gather_points_grad(int b, int c, int n, int npoints, const float *grad_out, const int *idx,
                                     float *grad_points, void *workspace, size_t workspace_bytes, hgStream stream_) {
+  HG_NVTX_RANGE("hg_p2_gather_points_grad");
   cudaStream_t stream = hg_stream(stream_);
   HG_REQUIRE(grad_out && idx && grad_points, HG_E_BADARG, "gather_points_grad: null pointer");
   HG_REQUIRE(b > 0 && c > 0 && n > 0 && npoints > 0, HG_E_BADARG, "gather_points_grad: sizes must be positive");
@@ -763,6 +765,7 @@ HG_API int hg_p2_gather_points_grad(int b, int c, int n, int npoints, const floa
 
 HG_API int hg_p2_furthest_point_sampling(int b, int n, int m, const float *dataset, float *temp, int *idxs,
                                          hgStream stream_) {
+  HG_NVTX_RANGE("hg_p2_furthest_point_sampling");
   (void)temp;  // the reference's global scratch (sampling.cpp:74-76); distances live in registers here
   HG_REQUIRE(dataset && idxs, HG_E_BADARG, "furthest_point_sampling: null pointer");
   HG_REQUIRE(b > 0 && n > 0 && m >= 0, HG_E_BADARG, "furthest_point_sampling: bad sizes");
@@ -772,6 +775,7 @@ HG_API int hg_p2_furthest_point_sampling(int b, int n, int m, const float *datas
 
 HG_API int hg_fps_torch_f32(const float *xyz, int B, int N, int npoint, const int64_t *start, int64_t *centroids,
                             hgStream stream_) {
+  HG_NVTX_RANGE("hg_fps_torch_f32");
   HG_REQUIRE(xyz && start && centroids, HG_E_BADARG, "fps_torch: null pointer");
   HG_REQUIRE(B > 0 && N > 0 && npoint >= 0, HG_E_BADARG, "fps_torch: bad sizes");
   if (npoint == 0) return HG_OK;
@@ -781,6 +785,7 @@ HG_API int hg_fps_torch_f32(const float *xyz, int B, int N, int npoint, const in
 
 HG_API int hg_p2_ball_query(int b, int n, int m, float radius, int nsample, const float *new_xyz, const float *xyz,
                             int *idx, hgStream stream_) {
+  HG_NVTX_RANGE("hg_p2_ball_query");
   HG_REQUIRE(new_xyz && xyz && idx, HG_E_BADARG, "ball_query: null pointer");
   HG_REQUIRE(b > 0 && n > 0 && m > 0 && nsample > 0, HG_E_BADARG, "ball_query: sizes must be positive");
   HG_REQUIRE(b <= 65535, HG_E_UNSUPPORTED, "ball_query: b=%d > 65535", b);
@@ -792,6 +797,7 @@ HG_API int hg_p2_ball_query(int b, int n, int m, float radius, int nsample, cons
 
 HG_API int hg_p2_group_points(int b, int c, int n, int npoints, int nsample, const float *points, const int *idx,
                               float *out, hgStream stream_) {
+  HG_NVTX_RANGE("hg_p2_group_points");
   HG_REQUIRE(points && idx && out, HG_E_BADARG, "group_points: null pointer");
   HG_REQUIRE(b > 0 && c > 0 && n > 0 && npoints > 0 && nsample > 0, HG_E_BADARG, "group_points: sizes must be positive");
   return launch_gather(points, idx, b, c, n, npoints * nsample, out, hg_stream(stream_), HG_PROF_GROUP);
@@ -801,6 +807,7 @@ HG_API int hg_p2_group_points(int b, int c, int n, int npoints, int nsample, con
 // new_xyz, rows 3.. = grouped features (the reference: two grouping ops, an in-place subtraction and a torch.cat)
 HG_API int hg_p2_group_concat(int b, int c, int n, int npoints, int nsample, const float *xyz, const float *new_xyz,
                               const float *features, const int *idx, float *out, hgStream stream_) {
+  HG_NVTX_RANGE("hg_p2_group_concat");
   cudaStream_t stream = hg_stream(stream_);
   HG_REQUIRE(xyz && new_xyz && idx && out, HG_E_BADARG, "group_concat: null pointer");
   HG_REQUIRE(b > 0 && c >= 0 && n > 0 && npoints > 0 && nsample > 0, HG_E_BADARG, "group_concat: bad sizes");
@@ -818,6 +825,7 @@ HG_API int hg_p2_group_concat(int b, int c, int n, int npoints, int nsample, con
 HG_API int hg_p2_group_concat_grad(int b, int c, int n, int npoints, int nsample, const float *grad_out, const int *idx,
                                    float *grad_xyz_t, float *grad_features, void *workspace, size_t workspace_bytes,
                                    hgStream stream_) {
+  HG_NVTX_RANGE("hg_p2_group_concat_grad");
   cudaStream_t stream = hg_stream(stream_);
   HG_REQUIRE(grad_out && idx && (grad_xyz_t || grad_features), HG_E_BADARG, "group_concat_grad: null pointer");
   HG_REQUIRE(b > 0 && c >= 0 && n > 0 && npoints > 0 && nsample > 0, HG_E_BADARG, "group_concat_grad: bad sizes");
@@ -841,6 +849,7 @@ HG_API int hg_p2_group_concat_grad(int b, int c, int n, int npoints, int nsample
 HG_API int hg_p2_group_points_grad(int b, int c, int n, int npoints, int nsample, const float *grad_out,
                                    const int *idx, float *grad_points, void *workspace, size_t workspace_bytes,
                                    hgStream stream_) {
+  HG_NVTX_RANGE("hg_p2_group_points_grad");
   cudaStream_t stream = hg_stream(stream_);
   HG_REQUIRE(grad_out && idx && grad_points, HG_E_BADARG, "group_points_grad: null pointer");
   HG_REQUIRE(b > 0 && c > 0 && n > 0 && npoints > 0 && nsample > 0, HG_E_BADARG,
@@ -857,6 +866,7 @@ HG_API int hg_p2_group_points_grad(int b, int c, int n, int npoints, int nsample
 
 HG_API int hg_p2_three_nn(int b, int n, int m, const float *unknown, const float *known, float *dist2, int *idx,
                           hgStream stream_) {
+  HG_NVTX_RANGE("hg_p2_three_nn");
   HG_REQUIRE(unknown && known && dist2 && idx, HG_E_BADARG, "three_nn: null pointer");
   HG_REQUIRE(b > 0 && n > 0 && m > 0, HG_E_BADARG, "three_nn: sizes must be positive");
   HG_REQUIRE(b <= 65535, HG_E_UNSUPPORTED, "three_nn: b=%d > 65535", b);
@@ -867,6 +877,7 @@ HG_API int hg_p2_three_nn(int b, int n, int m, const float *unknown, const float
 
 HG_API int hg_p2_three_interpolate(int b, int c, int m, int n, const float *points, const int *idx,
                                    const float *weight, float *out, hgStream stream_) {
+  HG_NVTX_RANGE("hg_p2_three_interpolate");
   HG_REQUIRE(points && idx && weight && out, HG_E_BADARG, "three_interpolate: null pointer");
   HG_REQUIRE(b > 0 && c > 0 && m > 0 && n > 0, HG_E_BADARG, "three_interpolate: sizes must be positive");
   const size_t smem = (size_t)kInterpCP * m * sizeof(float);
@@ -891,6 +902,7 @@ HG_API int hg_p2_three_interpolate(int b, int c, int m, int n, const float *poin
 HG_API int hg_p2_three_interpolate_grad(int b, int c, int n, int m, const float *grad_out, const int *idx,
                                         const float *weight, float *grad_points, void *workspace,
                                         size_t workspace_bytes, hgStream stream_) {
+  HG_NVTX_RANGE("hg_p2_three_interpolate_grad");
   cudaStream_t stream = hg_stream(stream_);
   HG_REQUIRE(grad_out && idx && weight && grad_points, HG_E_BADARG, "three_interpolate_grad: null pointer");
   HG_REQUIRE(b > 0 && c > 0 && m > 0 && n > 0, HG_E_BADARG, "three_interpolate_grad: sizes must be positive");

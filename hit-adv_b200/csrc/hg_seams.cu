@@ -218,6 +218,7 @@ __global__ void __launch_bounds__(256) index_points_grad_kernel(const float *__r
 
 HG_API int hg_square_distance_f32(const float *src, const float *dst, int B, int N, int M, int C, float *out,
                                   hgStream stream_) {
+  HG_NVTX_RANGE("hg_square_distance_f32");
   HG_REQUIRE(src && dst && out, HG_E_BADARG, "square_distance: null pointer");
   HG_REQUIRE(B > 0 && N > 0 && M > 0 && C > 0, HG_E_BADARG, "square_distance: sizes must be positive");
   if (C <= kSqMaxC && B <= 65535 && (N + kSqRows - 1) / kSqRows <= 65535) {
@@ -233,6 +234,7 @@ HG_API int hg_square_distance_f32(const float *src, const float *dst, int B, int
 
 HG_API int hg_query_ball_torch_f32(float radius2, int nsample, const float *xyz, const float *new_xyz, int B, int N,
                                    int S, int64_t *group_idx, hgStream stream_) {
+  HG_NVTX_RANGE("hg_query_ball_torch_f32");
   HG_REQUIRE(xyz && new_xyz && group_idx, HG_E_BADARG, "query_ball_torch: null pointer");
   HG_REQUIRE(B > 0 && N > 0 && S > 0 && nsample > 0, HG_E_BADARG, "query_ball_torch: sizes must be positive");
   HG_REQUIRE(B <= 65535, HG_E_UNSUPPORTED, "query_ball_torch: B=%d > 65535", B);
@@ -244,6 +246,7 @@ HG_API int hg_query_ball_torch_f32(float radius2, int nsample, const float *xyz,
 
 HG_API int hg_index_points_f32(const float *points, const int64_t *idx, int B, int N, int C, int M, float *out,
                                hgStream stream_) {
+  HG_NVTX_RANGE("hg_index_points_f32");
   HG_REQUIRE(points && idx && out, HG_E_BADARG, "index_points: null pointer");
   HG_REQUIRE(B > 0 && N > 0 && C > 0 && M > 0, HG_E_BADARG, "index_points: sizes must be positive");
   const long long total = (long long)B * M * C, rows = (long long)B * M;
@@ -269,6 +272,7 @@ HG_API size_t hg_index_points_grad_workspace_bytes(int B, int N, int M) {
 
 HG_API int hg_index_points_grad_f32(const float *grad_out, const int64_t *idx, int B, int N, int C, int M,
                                     float *grad_points, void *workspace, size_t workspace_bytes, hgStream stream_) {
+  HG_NVTX_RANGE("hg_index_points_grad_f32");
   cudaStream_t stream = hg_stream(stream_);
   HG_REQUIRE(grad_out && idx && grad_points, HG_E_BADARG, "index_points_grad: null pointer");
   HG_REQUIRE(B > 0 && N > 0 && C > 0 && M > 0, HG_E_BADARG, "index_points_grad: sizes must be positive");

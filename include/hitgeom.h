@@ -44,6 +44,8 @@ int hg_device_info(int *sm_count, int *clock_khz, long long *l2_bytes, long long
  * denominator bench.py reports next to the computed SMs x 128 x 2 x clock figure.  Synchronises the stream. */
 int hg_probe_fp32_peak(float *tflops, float *device_scratch, hgStream stream);
 
+/* Every compute entry point below opens an NVTX range named after itself (header-only NVTX v3: free unless nsys / ncu
+ * is attached), so a timeline of a reference run shows which reference call each kernel belongs to. */
 /* Optional device timing of the hot kernels (used by bench.py for the roofline line).  hg_prof_enable(1) resets
  * the counters and brackets every launch of a tagged kernel with CUDA events on the launching stream;
  * hg_prof_read synchronises those events and returns the summed device time [ms] and the launch count. */
