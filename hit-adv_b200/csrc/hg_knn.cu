@@ -21,6 +21,28 @@ __global__ void knn_sumsq_kernel(const float *__restrict__ pc, long long total, 
        g += (long long)gridDim.x * blockDim.x) {
     const float *a = pc + (size_t)g * C;
     float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
+    if ((C & 15) == 0 && (reinterpret_cast<uintptr_t>(pc) & 15) == 0) {  // same order, 16-byte loads, 16 channels per step
+      for (int c = 0; c < C; c += 16) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = __ldg(reinterpret_cast<const float4 *>(a + c) + u);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          acc0 = __fadd_rn(acc0, __fmul_rn(v[u].x, v[u].x));
+          acc0 = __fadd_rn(acc0, __fmul_rn(v[u].y, v[u].y));
+          acc0 = __fadd_rn(acc0, __fmul_rn(v[u].z, v[u].z));
+          acc0 = __fadd_rn(acc0, __fmul_rn(v[u].w, v[u].w));
+        }
+        acc1 = __fadd_rn(acc1, acc0);
+        acc0 = 0.f;
+        if (((c + 16) & 255) == 0) {
+          acc2 = __fadd_rn(acc2, acc1);
+          acc1 = 0.f;
+        }
+      }
+      xx[g] = __fadd_rn(__fadd_rn(acc0, acc1), acc2);
+      continue;
+    }
     for (int c = 0; c < C; ++c) {
       acc0 = __fadd_rn(acc0, __fmul_rn(a[c], a[c]));
       if (((c + 1) & 15) == 0) {
@@ -537,10 +559,10 @@ HG_API int hg_knn_self_temporal_f32(const float *pc, int B, int K, int C, int k1
   HG_CHECK_LAUNCH("knn_sumsq_kernel");
   // feature clouds of DGCNN's shapes: tensor-core filter fused with the exact FP32 evaluation (hg_knn_tc.cu); everything
   // else (and hg_tune("knn_tc", 1)) takes the FP32 distance tile + row select below
-  // (small batches leave the serial chain of a CTA exposed -- measured at K = 1024, C = 64: 16 clouds 103 us against
-  // 144 us, 8 clouds 100 against 95, 4 clouds 96 against 65 -- so fewer CTAs than half the SMs stay on the FP32 path
-  // unless hg_tune("knn_tc", 2) forces the tensor-core kernel)
-  const bool tc_fills = 2LL * B * ((K + 127) / 128) >= hg_sm_count() || g_hg_tune_knn_tc_off == 2;
+  // (small batches leave the serial chain of a CTA exposed -- measured at K = 1024, C = 64: 16 clouds 85 us against
+  // 143 us, 8 clouds 82 against 95, 4 clouds 79 against 65 -- so fewer CTAs than a quarter of the SMs stay on the FP32
+  // path unless hg_tune("knn_tc", 2) forces the tensor-core kernel)
+  const bool tc_fills = 4LL * B * ((K + 127) / 128) >= hg_sm_count() || g_hg_tune_knn_tc_off == 2 || g_hg_tune_knn_tc_off == 5;
   if (g_hg_tune_knn_tc_off != 1 && tc_fills && hg_knn_tc_supported(K, C, k1) && (reinterpret_cast<uintptr_t>(pc) & 15) == 0)
     return hg_knn_tc_run(pc, xx, B, K, C, k1, vals, idx, stream);
   const size_t per = (size_t)K * K * sizeof(float);

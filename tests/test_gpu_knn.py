@@ -214,7 +214,7 @@ def test_knn_outlier_backward_fused_and_general_paths_give_the_same_bits():
 
 
 # ---- tensor-core filter + exact evaluation (hg_knn_tc.cu): same values and indices as the FP32 path and the oracle --------------------
-@pytest.mark.parametrize("tc_off", [2, 1])
+@pytest.mark.parametrize("tc_off", [2, 5, 1])
 @pytest.mark.parametrize("C,K,k1,kind", [(64, 1024, 20, "gauss"), (128, 512, 20, "gauss"), (32, 300, 7, "gauss"),
                                          (96, 777, 32, "gauss"), (64, 512, 20, "prototypes"), (64, 640, 5, "scaled"),
                                          (128, 1024, 20, "dups")])

@@ -14,11 +14,11 @@ torch.manual_seed(0)
 for (B, C, N, k) in ((32, 64, 1024, 20), (32, 64, 1024, 20), (16, 64, 1024, 20), (4, 64, 1024, 20), (32, 128, 1024, 20), (32, 64, 2048, 20), (8, 64, 1024, 20), (32, 64, 1024, 5), (32, 32, 1024, 20)):
     x = torch.randn(B, C, N, device="cuda")
     res = {}
-    for off in (1, 2, 0):  # 1: FP32 path; 2: tensor-core path forced; 0: default dispatch
+    for off in (1, 2, 5, 0):  # 1: FP32 path; 2: tensor-core path forced; 5: forced, single-sweep threshold; 0: default dispatch
         _lib.lib().hg_tune(b"knn_tc", off)
         res[off] = (timeit(lambda: ms.knn(x, k), flush=flush), ms.knn(x, k))
     _lib.lib().hg_tune(b"knn_tc", 0)
-    same = all(torch.equal(res[m][1], res[1][1]) for m in (0, 2))
+    same = all(torch.equal(res[m][1], res[1][1]) for m in (0, 2, 5))
 
     def ref_knn():
         inner = -2 * torch.matmul(x.transpose(2, 1), x)
@@ -26,5 +26,5 @@ for (B, C, N, k) in ((32, 64, 1024, 20), (32, 64, 1024, 20), (16, 64, 1024, 20),
         return (-xx - inner - xx.transpose(2, 1)).topk(k=k, dim=-1)[1]
 
     t_ref = timeit(ref_knn, flush=flush)
-    print(f"DGCNN knn B={B} C={C} N={N} k={k}: FP32 path {res[1][0]*1e3:7.1f} us   tensor-core (forced) {res[2][0]*1e3:7.1f} us   default {res[0][0]*1e3:7.1f} us   "
+    print(f"DGCNN knn B={B} C={C} N={N} k={k}: FP32 path {res[1][0]*1e3:7.1f} us   tensor-core (forced) {res[2][0]*1e3:7.1f} us   single sweep {res[5][0]*1e3:7.1f} us   default {res[0][0]*1e3:7.1f} us   "
           f"torch matmul+topk {t_ref*1e3:7.1f} us   same indices: {same}", flush=True)
