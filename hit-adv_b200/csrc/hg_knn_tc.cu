@@ -17,7 +17,7 @@
 //
 // History (round 2): a two-kernel version -- two-pass filter writing candidate lists, then a warp-per-row exact kernel
 // gathering the candidates' rows from L2 -- took 163 us at 32 x 1024 x 64 (filter 50 us, gather-bound exact kernel 88 us);
-// the fused pass takes 131 us for the whole call (98 us the kernel).  A variant with two threads per row (16 warps per SM, two partial lists
+// the fused pass takes 99 us for the whole call (75 us the kernel; 130 us with a single sweep, see two_pass).  A variant with two threads per row (16 warps per SM, two partial lists
 // merged at the end) was slower (156 us): the exact phase is bound by shared-memory bandwidth (random candidate rows:
 // 1.9 wavefronts per ideal one), not by latency, and two lists admit more candidates than one.
 #include <cuda.h>
