@@ -17,8 +17,8 @@
 //
 // History (round 2): a two-kernel version -- two-pass filter writing candidate lists, then a warp-per-row exact kernel
 // gathering the candidates' rows from L2 -- took 163 us at 32 x 1024 x 64 (filter 50 us, gather-bound exact kernel 88 us);
-// the fused pass takes 99 us for the whole call (75 us the kernel; 130 us with a single sweep, see two_pass).  A variant with two threads per row (16 warps per SM, two partial lists
-// merged at the end) was slower (156 us): the exact phase is bound by shared-memory bandwidth (random candidate rows:
+// the fused pass takes 99 us for the whole call (75 us the kernel; 130 us with a single sweep, see two_pass).  A variant
+// with two threads per row (16 warps per SM, two partial lists merged at the end) was slower (156 us against 135): the exact phase is bound by shared-memory bandwidth (random candidate rows:
 // 1.9 wavefronts per ideal one), not by latency, and two lists admit more candidates than one.
 #include <cuda.h>
 
@@ -107,10 +107,11 @@ __host__ __device__ constexpr uint32_t tc_idesc(int M, int N) {
 // with conflict-free 16-byte loads, runs the reference's sequential FMA chain and inserts (value, index) into a sorted
 // register list of the row's KM smallest.  Columns are visited in ascending order, so a strict '<' insertion keeps the
 // lowest index among equal values (torch.topk's order on this path, hg_knn.cu).  The admission threshold starts from
-// the k-th smallest of 32 column-class minima of tile 0 (an upper bound on the k-th smallest approximate distance) and
-// follows the list's k-th EXACT value from then on:  approx_j <= (k-th exact so far) + 2 eps  is necessary for column j
-// to enter the final list, eps bounding |approximate - reference| for the row (header).  One pass over the tiles:
-// half the TMA traffic and MMAs of the two-pass filter, no candidate lists in global memory, no L2 gathers.
+// the k-th smallest of 32 column-class minima (an upper bound on the k-th smallest approximate distance) -- taken over
+// ALL columns by a first, MMA-only sweep (two_pass, the default), or over tile 0 only -- and follows the list's k-th
+// EXACT value from then on:  approx_j <= (k-th exact so far) + 2 eps  is necessary for column j to enter the final
+// list, eps bounding |approximate - reference| for the row (header).  The first sweep costs a second round of TMA loads
+// and MMAs and halves the exact evaluations (130 -> 99 us).  No candidate lists in global memory, no L2 gathers.
 template <int KM>
 struct TcList {
   float v[KM];
