@@ -58,6 +58,27 @@ __global__ void knn_sumsq_kernel(const float *__restrict__ pc, long long total, 
   }
 }
 
+// 3-D clouds with long neighbour lists (DGCNN layer 1: k = 20) on the tensor-core kernel: the cloud is copied into 32-channel
+// rows (x, y, z, 0, ...: a 128-byte row is what the TMA boxes of hg_knn_tc.cu move) and the squared norms are taken with
+// the 3-D kernels' operation order.  The zero channels change nothing in the reference's FMA chain (fma(0, 0, acc) = acc),
+// so values and indices are the 3-D path's bit for bit.
+constexpr int kPadC = 32;
+__global__ void __launch_bounds__(256) knn_pad3_kernel(const float *__restrict__ pc, long long total,
+                                                       float4 *__restrict__ padded, float *__restrict__ xx) {
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total * (kPadC / 4);
+       g += (long long)gridDim.x * blockDim.x) {
+    const long long row = g / (kPadC / 4);
+    const int q = (int)(g - row * (kPadC / 4));
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (q == 0) {
+      const float x = __ldg(pc + row * 3), y = __ldg(pc + row * 3 + 1), z = __ldg(pc + row * 3 + 2);
+      v = make_float4(x, y, z, 0.f);
+      xx[row] = hg_sumsq3_seq(x, y, z);
+    }
+    padded[g] = v;
+  }
+}
+
 // dist tile: 128 rows x 128 columns per CTA, 8 x 8 per thread (columns as four packed pairs), channels consumed strictly
 // in order: every accumulator is the reference's sequential FMA chain (product of channel 0 first, then c = 1..C-1).
 // Per channel a thread reads 8 row values (two broadcast LDS.128) and 8 column values (two LDS.128) for 32 FFMA2:
@@ -521,10 +542,17 @@ constexpr size_t kGenericScratchBytes = (size_t)256 << 20;
 
 }  // namespace
 
+// 3-D self-kNN shapes that may take the tensor-core kernel on a padded copy (the dispatch also looks at the batch size)
+static bool knn3_pad_candidate(int K, int k1) { return k1 >= 12 && hg_knn_tc_supported(K, kPadC, k1); }
+
 HG_API size_t hg_knn_self_workspace_bytes(int B, int K, int C, int k1) {
-  (void)k1;
   if (B <= 0 || K <= 0 || C <= 0) return 0;
-  if (C == 3) return hg_knn3_seed_workspace_bytes(B, K);
+  if (C == 3) {
+    size_t w = hg_knn3_seed_workspace_bytes(B, K);
+    if (knn3_pad_candidate(K, k1))  // padded copy + squared norms for the tensor-core kernel
+      w += hg_align((size_t)B * K * kPadC * sizeof(float)) + hg_align((size_t)B * K * sizeof(float));
+    return w;
+  }
   size_t per = (size_t)K * K * sizeof(float);
   size_t nb = kGenericScratchBytes / per;
   if (nb < 1) nb = 1;
@@ -547,8 +575,25 @@ HG_API int hg_knn_self_temporal_f32(const float *pc, int B, int K, int C, int k1
   HG_REQUIRE(k1 >= 1 && k1 <= (C == 3 ? 64 : 32) && k1 <= K, HG_E_BADARG,
              "knn_self: need 1 <= k <= min(%d, K); got k=%d K=%d", C == 3 ? 64 : 32, k1, K);
   HG_REQUIRE(B <= 65535, HG_E_UNSUPPORTED, "knn_self: B=%d > 65535 clouds per call", B);
-  if (C == 3)
+  if (C == 3) {
+    // long lists on enough clouds to fill the machine: the tensor-core kernel on a 32-channel copy beats the 3-D
+    // small-cloud kernel up to ~8 CTAs per SM (k = 20, 1024 points: 16 clouds 62 against 131 us, 32: 78 / 136, 128: 221 / 236,
+    // 192: 326 / 313; 2048 points: 32 clouds 196 / 244, 96: 485 / 464); KNNDist's short lists (and its temporal state) stay 3-D
+    const size_t seed_ws = hg_knn3_seed_workspace_bytes(B, K);
+    const size_t pad_ws = hg_align((size_t)B * K * kPadC * sizeof(float)) + hg_align((size_t)B * K * sizeof(float));
+    if (!idx_state && knn3_pad_candidate(K, k1) && g_hg_tune_knn_tc_off != 1 && workspace &&
+        workspace_bytes >= seed_ws + pad_ws &&
+        ((4LL * B * ((K + 127) / 128) >= hg_sm_count() && (long long)B * ((K + 127) / 128) <= 8LL * hg_sm_count()) ||
+         g_hg_tune_knn_tc_off == 2 || g_hg_tune_knn_tc_off == 5)) {
+      float *padded = (float *)((char *)workspace + seed_ws);
+      float *xxp = (float *)((char *)padded + hg_align((size_t)B * K * kPadC * sizeof(float)));
+      const long long rows = (long long)B * K;
+      knn_pad3_kernel<<<grid_for(rows * (kPadC / 4), 256), 256, 0, stream>>>(pc, rows, (float4 *)padded, xxp);
+      HG_CHECK_LAUNCH("knn_pad3_kernel");
+      return hg_knn_tc_run(padded, xxp, B, K, kPadC, k1, vals, idx, stream);
+    }
     return hg_knn3_self_seeded_i32(pc, B, K, k1, vals, idx, workspace, workspace_bytes, stream, idx_state, state_valid);
+  }
   const size_t need = hg_knn_self_workspace_bytes(B, K, C, k1);
   HG_REQUIRE(workspace && workspace_bytes >= need, HG_E_WORKSPACE, "knn_self: workspace too small (%zu < %zu)",
              workspace_bytes, need);

@@ -247,3 +247,28 @@ def test_knn_feature_clouds_tensor_core_vs_oracle(oracle, F, C, K, k1, kind, tc_
     ov, oi = oracle.knn_self(pc, k1, threads=2)
     assert np.array_equal(idx.cpu().numpy(), oi), (kind, "indices")
     assert np.array_equal(vals.cpu().numpy(), ov), (kind, "values")
+
+
+@pytest.mark.parametrize("K,k1", [(1024, 20), (777, 12), (2048, 32), (300, 21)])
+def test_knn_3d_long_lists_on_the_tensor_core_kernel_vs_oracle(oracle, F, K, k1):
+    """3-D clouds with long neighbour lists (DGCNN layer 1, k = 20) take the tensor-core kernel on a 32-channel padded copy
+    when the batch fills the machine (`hg_tune("knn_tc", 2)` forces it here): the zero channels change nothing in the
+    reference's FMA chain, so values and indices are the 3-D kernels' and the oracle's bit for bit -- surface clouds with
+    exact duplicates, a cloud far from the origin (large norms: the TF32 error bound is per row), identical points."""
+    from hitgeom._lib import lib
+
+    a = clouds(3, K, 300 + K, "surface")
+    a[1, : K // 4] = a[1, K // 4 : 2 * (K // 4)]
+    a[2, : K // 2] = a[2, 0]
+    b = (clouds(2, K, 77 + K, "gauss") * 0.05 + np.asarray((60.0, -35.0, 20.0), np.float32)).astype(np.float32)
+    for tag, pc in (("surface+dups", a), ("far from origin", b)):
+        ov, oi = oracle.knn_self(pc, k1, threads=2)
+        outs = {}
+        for knob in (2, 1):  # tensor-core kernel forced / switched off (3-D small-cloud kernel)
+            lib().hg_tune(b"knn_tc", knob)
+            try:
+                vals, idx = F.knn_self(gpu(pc), k1)
+            finally:
+                lib().hg_tune(b"knn_tc", 0)
+            assert np.array_equal(idx.cpu().numpy(), oi), (tag, knob, "indices")
+            assert np.array_equal(vals.cpu().numpy(), ov), (tag, knob, "values")

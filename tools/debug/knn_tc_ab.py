@@ -11,7 +11,9 @@ from bench_ops import timeit
 
 flush = (torch.empty(256 << 20, dtype=torch.uint8, device="cuda"), torch.zeros(64 << 20, dtype=torch.float32, device="cuda"))
 torch.manual_seed(0)
-for (B, C, N, k) in ((32, 64, 1024, 20), (32, 64, 1024, 20), (16, 64, 1024, 20), (4, 64, 1024, 20), (32, 128, 1024, 20), (32, 64, 2048, 20), (8, 64, 1024, 20), (32, 64, 1024, 5), (32, 32, 1024, 20)):
+import sys
+SH = [(96, 3, 1024, 20), (128, 3, 1024, 20), (192, 3, 1024, 20), (388, 3, 1024, 20), (128, 3, 1024, 12), (96, 3, 2048, 20)] if 'c3' in sys.argv else None
+for (B, C, N, k) in SH or ((32, 64, 1024, 20), (32, 64, 1024, 20), (16, 64, 1024, 20), (4, 64, 1024, 20), (32, 128, 1024, 20), (32, 64, 2048, 20), (8, 64, 1024, 20), (32, 64, 1024, 5), (32, 32, 1024, 20), (32, 3, 1024, 20), (64, 3, 1024, 20), (32, 3, 1024, 12), (32, 3, 2048, 20), (16, 3, 1024, 20)):
     x = torch.randn(B, C, N, device="cuda")
     res = {}
     for off in (1, 2, 5, 0):  # 1: FP32 path; 2: tensor-core path forced; 5: forced, single-sweep threshold; 0: default dispatch
