@@ -3,9 +3,10 @@
 // One call = what a CW-kNN attack iteration asks of the distance term (CW/kNN.py:104-108 with
 // util/dist_utils.py:258-294 ChamferkNNDist, batch_avg=True): adversarial and original clouds in host memory ->
 // loss (host scalar) and d loss / d adv (host array).  The batch is cut into chunks of clouds (clouds are
-// independent) that are pipelined over two streams, each with its own device buffers:
-// while chunk i computes, chunk i+1 is copied in and the gradient of chunk i-1 is copied out, so PCIe/NVLink-C2C
-// traffic disappears behind the kernels instead of adding to them.  The kernels are the same entry points the
+// independent) that go through two sets of device buffers: all kernels run back to back on ONE
+// compute stream (kernels of two chunks on two streams only contend: 117.3 -> 116.4 ms per config-5 step), the copies of
+// a buffer set on its own stream, events in between: while chunk i computes, chunk i+1 is copied in and the gradient of
+// chunk i-1 is copied out, so PCIe/NVLink-C2C traffic disappears behind the kernels instead of adding to them.  The kernels are the same entry points the
 // device-pointer ABI exposes (hg_nn_bidir_f32, hg_set_loss_*, hg_knn_self_f32, hg_knn_outlier_*): results are
 // bit-identical to calling those on a resident batch.
 #include <new>
@@ -16,9 +17,12 @@ struct hgHostStep {
   int N = 0, chunk = 0, k1max = 0, device = 0;
   float *loss_pinned = nullptr;  // [loss_cap] page-locked staging for the per-cloud losses: a D2H copy into pageable
   int loss_cap = 0;              // memory would block the host inside the loop and serialise the pipeline
+  cudaStream_t compute = nullptr;  // all kernels, back to back (two streams of kernels would only contend)
   struct Slot {
-    cudaStream_t stream = nullptr;
-    cudaEvent_t done = nullptr;  // D2H of the previous use of this slot finished
+    cudaStream_t stream = nullptr;   // this slot's copies, both directions
+    cudaEvent_t done = nullptr;      // (unused) D2H of the previous use of this slot finished
+    cudaEvent_t in_ready = nullptr;  // this slot's host-to-device copies have landed
+    cudaEvent_t comp_done = nullptr; // this slot's kernels have finished
     float *adv = nullptr, *ori = nullptr, *grad_ch = nullptr, *grad_knn = nullptr;
     float *min1 = nullptr, *min2 = nullptr, *vals = nullptr, *value = nullptr, *mask = nullptr;
     int *arg1 = nullptr, *arg2 = nullptr, *idx = nullptr;
@@ -93,17 +97,23 @@ void free_session(hgHostStep *s) {
       if (p) cudaFree(p);
     if (sl.ws) cudaFree(sl.ws);
     if (sl.done) cudaEventDestroy(sl.done);
+    if (sl.in_ready) cudaEventDestroy(sl.in_ready);
+    if (sl.comp_done) cudaEventDestroy(sl.comp_done);
     if (sl.stream) cudaStreamDestroy(sl.stream);
   }
+  if (s->compute) cudaStreamDestroy(s->compute);
   if (s->loss_pinned) cudaFreeHost(s->loss_pinned);
   delete s;
 }
 
 int init_session(hgHostStep *s) {
   const size_t pts = (size_t)s->chunk * s->N;
+  HG_CUDA(cudaStreamCreateWithFlags(&s->compute, cudaStreamNonBlocking));
   for (auto &sl : s->slot) {
     HG_CUDA(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
     HG_CUDA(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+    HG_CUDA(cudaEventCreateWithFlags(&sl.in_ready, cudaEventDisableTiming));
+    HG_CUDA(cudaEventCreateWithFlags(&sl.comp_done, cudaEventDisableTiming));
     int rc = 0;
     rc |= dev_alloc(&sl.adv, pts * 3) | dev_alloc(&sl.ori, pts * 3) | dev_alloc(&sl.grad_ch, pts * 3) |
           dev_alloc(&sl.grad_knn, pts * 3);
@@ -170,12 +180,15 @@ HG_API int hg_chamfer_knn_step_host_f32(hgHostStep *s, const float *adv_h, const
     auto &sl = s->slot[use];
     const int nb = (B - b0 < s->chunk) ? (B - b0) : s->chunk;
     const size_t pts = (size_t)nb * N, off = (size_t)b0 * N * 3;
-    cudaStream_t st = sl.stream;
+    // copies on the slot's stream, kernels on the one compute stream, events in between.  The slot stream's order
+    // already guarantees that this slot's previous D2H finished before its buffers are rewritten.
+    cudaStream_t cp = sl.stream, st = s->compute;
     hgStream hs = (hgStream)st;
-    // (stream order already guarantees that this slot's previous D2H finished before its buffers are rewritten)
-    HG_CUDA(cudaMemcpyAsync(sl.adv, adv_h + off, pts * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
-    HG_CUDA(cudaMemcpyAsync(sl.ori, ori_h + off, pts * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
-    if (weights_h) HG_CUDA(cudaMemcpyAsync(sl.w, weights_h + b0, (size_t)nb * sizeof(float), cudaMemcpyHostToDevice, st));
+    HG_CUDA(cudaMemcpyAsync(sl.adv, adv_h + off, pts * 3 * sizeof(float), cudaMemcpyHostToDevice, cp));
+    HG_CUDA(cudaMemcpyAsync(sl.ori, ori_h + off, pts * 3 * sizeof(float), cudaMemcpyHostToDevice, cp));
+    if (weights_h) HG_CUDA(cudaMemcpyAsync(sl.w, weights_h + b0, (size_t)nb * sizeof(float), cudaMemcpyHostToDevice, cp));
+    HG_CUDA(cudaEventRecord(sl.in_ready, cp));
+    HG_CUDA(cudaStreamWaitEvent(st, sl.in_ready, 0));
     int rc = hg_nn_bidir_f32(sl.ori, sl.adv, nb, N, N, 3, sl.min1, sl.arg1, sl.min2, sl.arg2, sl.ws, sl.ws_bytes, hs);
     if (rc) return rc;
     rc = hg_set_loss_f32(sl.min1, sl.min2, nb, N, N, HG_MODE_CHAMFER, sl.loss1, sl.loss2, nullptr, nullptr, hs);
@@ -202,11 +215,14 @@ HG_API int hg_chamfer_knn_step_host_f32(hgHostStep *s, const float *adv_h, const
       host_step_add_kernel<<<(int)blocks, 256, 0, st>>>(sl.grad_ch, sl.grad_knn, n);
       HG_CHECK_LAUNCH("host_step_add_kernel");
     }
-    HG_CUDA(cudaMemcpyAsync(grad_adv_h + off, sl.grad_ch, pts * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
-    HG_CUDA(cudaMemcpyAsync(s->loss_pinned + b0, sl.total, (size_t)nb * sizeof(float), cudaMemcpyDeviceToHost, st));
+    HG_CUDA(cudaEventRecord(sl.comp_done, st));
+    HG_CUDA(cudaStreamWaitEvent(cp, sl.comp_done, 0));
+    HG_CUDA(cudaMemcpyAsync(grad_adv_h + off, sl.grad_ch, pts * 3 * sizeof(float), cudaMemcpyDeviceToHost, cp));
+    HG_CUDA(cudaMemcpyAsync(s->loss_pinned + b0, sl.total, (size_t)nb * sizeof(float), cudaMemcpyDeviceToHost, cp));
   }
   HG_CUDA(cudaStreamSynchronize(s->slot[0].stream));
   HG_CUDA(cudaStreamSynchronize(s->slot[1].stream));
+  HG_CUDA(cudaStreamSynchronize(s->compute));
   double acc = 0.0;
   for (int b = 0; b < B; ++b) {
     cloud_loss_h[b] = s->loss_pinned[b];
