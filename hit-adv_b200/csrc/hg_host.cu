@@ -10,6 +10,7 @@
 // device-pointer ABI exposes (hg_nn_bidir_f32, hg_set_loss_*, hg_knn_self_f32, hg_knn_outlier_*): results are
 // bit-identical to calling those on a resident batch.
 #include <new>
+#include <vector>
 
 #include "hg_common.cuh"
 
@@ -175,10 +176,37 @@ HG_API int hg_chamfer_knn_step_host_f32(hgHostStep *s, const float *adv_h, const
     HG_CUDA(cudaMallocHost((void **)&s->loss_pinned, (size_t)B * sizeof(float)));
     s->loss_cap = B;
   }
-  int use = 0;
-  for (int b0 = 0; b0 < B; b0 += s->chunk, use ^= 1) {
+  // chunk schedule: short chunks at both ends -- the first chunk's host-to-device copy and the last chunk's
+  // device-to-host copy are the only transfers nothing can hide behind -- full-size chunks in between (fewer launches
+  // and kernel tails): 1024 clouds in slots of 256 go as 32, 96, 256, 256, 256, 96, 32 (116.5 -> 114.9 ms per step)
+  std::vector<int> sched;
+  {
+    const int c = s->chunk, head[2] = {c / 8 > 0 ? c / 8 : 1, (3 * c) / 8 > 0 ? (3 * c) / 8 : 1};
+    int left = B;
+    if (B >= 2 * c) {
+      for (int h = 0; h < 2; ++h) {
+        sched.push_back(head[h]);
+        left -= 2 * head[h];
+      }
+      while (left > 0) {
+        const int nb = left < c ? left : c;
+        sched.push_back(nb);
+        left -= nb;
+      }
+      sched.push_back(head[1]);
+      sched.push_back(head[0]);
+    } else {
+      while (left > 0) {
+        const int nb = left < c ? left : c;
+        sched.push_back(nb);
+        left -= nb;
+      }
+    }
+  }
+  int use = 0, b0 = 0;
+  for (size_t ci = 0; ci < sched.size(); b0 += sched[ci], ++ci, use ^= 1) {
     auto &sl = s->slot[use];
-    const int nb = (B - b0 < s->chunk) ? (B - b0) : s->chunk;
+    const int nb = sched[ci];
     const size_t pts = (size_t)nb * N, off = (size_t)b0 * N * 3;
     // copies on the slot's stream, kernels on the one compute stream, events in between.  The slot stream's order
     // already guarantees that this slot's previous D2H finished before its buffers are rewritten.

@@ -10,7 +10,8 @@ from util_inputs import clouds, jitter
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("B,N,chunk,method,k", [(10, 512, 4, "adv2ori", 5), (7, 1024, 16, "both", 4), (5, 300, 2, "ori2adv", 3)])
+@pytest.mark.parametrize("B,N,chunk,method,k", [(10, 512, 4, "adv2ori", 5), (7, 1024, 16, "both", 4), (5, 300, 2, "ori2adv", 3),
+                                                  (43, 256, 16, "adv2ori", 5)])
 def test_host_step_equals_device_path(B, N, chunk, method, k):
     from hitgeom.dist_utils import ChamferkNNDist
     from hitgeom.host import ChamferKnnHostStep

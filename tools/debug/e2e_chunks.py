@@ -12,7 +12,7 @@ ori /= np.linalg.norm(ori, axis=-1).max(axis=1)[:, None, None]
 adv = (ori + 0.01 * rng.standard_normal(ori.shape).astype(np.float32)).astype(np.float32)
 ori_h, adv_h = torch.from_numpy(ori).pin_memory(), torch.from_numpy(adv).pin_memory()
 grad_h = torch.empty_like(adv_h).pin_memory()
-for chunk in (64, 128, 256, 512):
+for chunk in (128, 256, 512):
     step = ChamferKnnHostStep(N, chunk_clouds=chunk)
     cl = np.empty(B, dtype=np.float32)
     for _ in range(2):
