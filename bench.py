@@ -352,10 +352,10 @@ def distance_record(workload, B, N, name, steps, warmup, rank, world, local, wit
         # config 1 is ~0.3 ms of kernel work behind ~25 launches: launch-bound.  An attack loop replays the step as a
         # CUDA graph (hitgeom.cw_knn graph=True); time that, and report the eager figure next to it.
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-        for s_, e_ in evs:  # the eager figure first (launch by launch, same streams): informational only
+        for s_, e_ in evs:  # the eager figure first (launch by launch, one stream: CPU-bound): informational only
             l2_flush()
             s_.record()
-            fwd_bwd()
+            fwd_bwd_serial()
             e_.record()
         torch.cuda.synchronize()
         eager_ms = sorted(s_.elapsed_time(e_) for s_, e_ in evs)[len(evs) // 2]
