@@ -495,7 +495,7 @@ def distance_record(workload, B, N, name, steps, warmup, rank, world, local, wit
             # the C ABI's host-buffer entry point: chunks of clouds, copies on their own streams behind the kernels
             from hitgeom.host import ChamferKnnHostStep
 
-            host_step = ChamferKnnHostStep(N, chunk_clouds=min(256, B))
+            host_step = ChamferKnnHostStep(N, chunk_clouds=min(512, B))
             cloud_loss_h = np.empty(B, dtype=np.float32)
 
             def e2e_step():
@@ -520,7 +520,7 @@ def distance_record(workload, B, N, name, steps, warmup, rank, world, local, wit
                "h2d_bytes_per_step": int(adv_h.numel() * 4 + ori_h.numel() * 4),
                "d2h_bytes_per_step": int(grad_h.numel() * 4 + (4 if small else 4 * B)), "loss": e2e_loss,
                "api": "pinned host buffers -> captured step (module calls) -> pinned host gradient + loss" if small else
-                      "hg_chamfer_knn_step_host_f32 (C ABI, host buffers, chunks of up to 256 clouds, short ones at both ends: one compute stream, copies on two copy streams)"}
+                      "hg_chamfer_knn_step_host_f32 (C ABI, host buffers, chunks of up to 512 clouds, short ones at both ends: one compute stream, copies on two copy streams)"}
 
     pk, pk_src = peaks()
     info = _lib.device_info()
