@@ -9,7 +9,7 @@ from bench import make_clouds
 from bench_ops import timeit
 
 flush = (torch.empty(256 << 20, dtype=torch.uint8, device="cuda"), torch.zeros(64 << 20, dtype=torch.float32, device="cuda"))
-for B, N in ((388, 1024), (128, 2048), (64, 4096), (32, 8192)):
+for B, N in ((388, 1024), (128, 2048), (64, 4096), (256, 16384)):
     ori, adv = make_clouds(B, N, 3)
     ori, adv = torch.from_numpy(ori).cuda(), torch.from_numpy(adv).cuda()
     F.tune_nn_bidir(0, 0)
@@ -18,7 +18,7 @@ for B, N in ((388, 1024), (128, 2048), (64, 4096), (32, 8192)):
     base2 = timeit(lambda: F.nn_bidir(ori, adv), flush=flush)
     print(f"B={B} N={N}: auto {base * 1e3:.1f} / {base2 * 1e3:.1f} us", flush=True)
     for T in (8, 16):
-        for RB in (64, 128, 256, 512):
+        for RB in (128, 256, 512, 1024):
             if RB > N:
                 continue
             F.tune_nn_bidir(T, RB)
