@@ -55,7 +55,8 @@ int hg_probe_fp32_peak(float *tflops, float *device_scratch, hgStream stream);
 #define HG_PROF_GROUP 3    /* gather_channel_major_kernel (group_points / gather_points) */
 #define HG_PROF_NTAGS 4
 /* Development knobs for A/B measurements (not part of the stable ABI): "scatter" = 0 auto / 1 staged / 2 bulk-copy;
- * "knn_tc" = 1 switches the tensor-core kNN kernel of feature clouds off, 2 forces it for small batches;
+ * "knn_tc" = 1 switches the tensor-core kNN kernel off, 2 forces it for small batches, 5 forces it with the
+ * single-sweep threshold;
  * "nn_exact" = 0 runs the experimental 4-operation approximate tracker (+ exact recovery) in hg_nn_bidir_f32
  * instead of the default 5-operation exact tracker (same results; see hg_nn_bidir.cu for why it is not the default);
  * "small_fused" = 1 sends clouds that fit in shared memory down the general finish / kNN-backward kernels as well
